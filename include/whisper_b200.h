@@ -1,0 +1,131 @@
+/*
+ * whisper_b200.h -- C-ABI of libwhisper_b200.so, the B200 (sm_100a) drop-in for the Whisper hot
+ * path of szuwgh/whisper.rs.
+ *
+ * The reference exposes no FFI/plugin interface: its boundary is three crate-private Rust
+ * functions sharing one context struct.  Each entry point below names the
+ * reference item it replaces (file:line in /root/reference, all in src/main.rs).  A Rust `-sys`
+ * crate binds exactly these symbols (whisper.rs_b200/rust/).
+ *
+ * Conventions: opaque handle; caller-owned host buffers (plain pointers + sizes); `int` return,
+ * 0 = ok, negative = a WsError variant (src/main.rs:50-72); one handle <-> one CUDA device + one
+ * stream; a handle is thread-compatible, not thread-safe (the reference's `&mut WhisperContext`).
+ * There is NO CPU fallback: every compute call fails with WB_ERR_TENSOR_OP when no sm_100 device
+ * is usable.
+ */
+#ifndef WHISPER_B200_H
+#define WHISPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb_ctx wb_ctx;
+
+/* WsError (src/main.rs:50-72) */
+enum {
+  WB_OK = 0,
+  WB_ERR_UNEXPECTED = -1,         /* WsError::Unexpected */
+  WB_ERR_IO = -2,                 /* WsError::UnexpectIO */
+  WB_ERR_BAD_MAGIC = -3,          /* WsError::BadMagic */
+  WB_ERR_NOT_ENOUGH_SPACE = -4,   /* WsError::NotEnoughSpace (batch / context capacity exceeded) */
+  WB_ERR_UNKNOWN_TENSOR = -5,     /* WsError::UnknownTensor */
+  WB_ERR_BAD_REF_TENSOR = -6,     /* WsError::BadRefTensor */
+  WB_ERR_WRONG_SIZE_TENSOR = -7,  /* WsError::WrongSizeTensor */
+  WB_ERR_WRONG_SHAPE_TENSOR = -8, /* WsError::WrongShapeTensor */
+  WB_ERR_WRONG_BYTES_TENSOR = -9, /* WsError::WrongBytesTensor */
+  WB_ERR_TENSOR_OP = -10          /* WsError::WrongGTensor: a device/kernel failure */
+};
+
+enum { WB_NORM_CLIP = 0, WB_NORM_SEGMENT = 1 };
+
+typedef struct wb_config {
+  int32_t device;          /* CUDA ordinal */
+  int32_t max_segments;    /* encoder/decoder batch capacity (30 s windows per wb_encode call) */
+  int32_t max_clips;       /* clips per wb_pcm_to_mel call */
+  int64_t max_clip_samples;/* longest clip, in samples */
+  int32_t norm_scope;      /* WB_NORM_CLIP = whole-clip max as clamp_and_normalize (1654-1671) */
+  int32_t checkpoints;     /* 1: keep sum|x| probes per stage (the author's debug probes, 1836-1849) */
+  void*   stream;          /* cudaStream_t to run on; NULL = the library creates its own */
+  int32_t decode_capacity; /* 1: allocate self-attention KV for max_segments sequences */
+  int32_t reserved[7];
+} wb_config;
+
+typedef struct wb_timings {  /* t_*_us of WhisperContext (src/main.rs:334-339), device-timed */
+  int64_t t_load_us, t_mel_us, t_sample_us, t_encode_us, t_decode_us;
+  int64_t n_mel_calls, n_encode_calls, n_decode_calls, n_kernel_launches;
+} wb_timings;
+
+/* stages of wb_checksum: the sum|x| probes the reference's author compared against whisper.cpp
+ * (src/main.rs:1439-1454, 1836-1849, 1998-2010, 2032-2058) */
+enum {
+  WB_STAGE_MEL = 0, WB_STAGE_CONV1 = 1, WB_STAGE_CONV2_POS = 2, WB_STAGE_LAYER = 3,
+  WB_STAGE_LN_POST = 4, WB_STAGE_CROSS_K = 5, WB_STAGE_CROSS_V = 6
+};
+
+void wb_config_default(wb_config* cfg);
+
+/* WhisperContext::new (366-503): parse the ggml-v1 file (magic 368-371, hparams 622-658, filters
+ * 513-535, vocab 578-592, tensor records 1381-1481 with the checks of 1401-1434), upload the
+ * weights, size every activation buffer from hparams (the MEM_REQ_* tables 117-189 are not used). */
+int wb_ctx_create(const char* model_path, const wb_config* cfg, wb_ctx** out);
+void wb_ctx_free(wb_ctx* ctx);
+int wb_get_hparams(const wb_ctx* ctx, int32_t out[11]);           /* WhisperHparams 607-619 */
+int wb_get_special_tokens(const wb_ctx* ctx, int32_t out[8]);     /* WhisperVocab ids 557-575, 433-440:
+                                                                      eot,sot,prev,solm,not,beg,translate,transcribe */
+
+/* whisper_pcm_to_mel (1681-1707) -> log_mel_spectrogram (1554-1652) + clamp_and_normalize
+ * (1654-1671), for n_clips clips of n_samples each.  The result stays on the device, like
+ * ctx.mel (349).  `pcm` is a HOST pointer ([n_clips][n_samples] f32); the _device variant takes a
+ * device pointer (inputs already resident in HBM). */
+int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips);
+int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, int n_clips);
+/* same with i16 PCM, the reference's real input: convert_integer_to_float_audio (1673-1679) */
+int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_clips);
+int wb_mel_dims(const wb_ctx* ctx, int* n_mel, int* n_len, int* n_clips);
+int wb_mel_read(wb_ctx* ctx, int clip, float* out, size_t cap_floats);   /* [n_mel][n_len], layout of 1633 */
+int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clips); /* set ctx.mel directly */
+
+/* whisper_encode (1799-2063), batched: segment s encodes the 2*n_ctx-frame window starting at
+ * mel_offsets[s] of clip clip_ids[s] (NULL = clip 0 / offset 0).  n_segments = 1, offset 0
+ * reproduces the reference's call (2074).  Leaves ln_post output and the per-layer cross-attention
+ * K/V (memory_cross_k/v, 1990-2030) on the device. */
+int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, int n_segments);
+int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out);        /* `cur` after ln_post (1980-1984): [n_ctx][d] f32 */
+int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v); /* F16 bits [n_ctx][d], 2018-2030 */
+int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum);
+
+/* The decode step the reference declares state for but never implements (694-731, 1336-1354,
+ * logits/probs 351-352): tokens is HOST [n_seqs][n_tokens]; sequence i attends to the cross K/V
+ * of encoder segment i.  Logits of the last position stay on the device. */
+int wb_decode(wb_ctx* ctx, const int32_t* tokens, int n_tokens, int n_past, int n_seqs);
+int wb_logits_read(wb_ctx* ctx, int seq, float* out);             /* [n_vocab] f32 */
+/* greedy loop on the device: arg-max over all logits, stop per sequence at `eot` or max_new.
+ * out_tokens [n_seqs][max_new], out_margin (top1 - top2 logit, may be NULL), out_len [n_seqs]. */
+int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_new, int eot,
+                     int n_seqs, int32_t* out_tokens, float* out_margin, int32_t* out_len);
+
+int wb_sync(wb_ctx* ctx);                                         /* wait for the handle's stream */
+int wb_timings_get(const wb_ctx* ctx, wb_timings* out);           /* t_*_us 334-339 */
+const char* wb_last_error(const wb_ctx* ctx);                     /* WsError Display text (52-71); ctx may be NULL */
+const char* wb_version(void);
+
+/* ---- parity / measurement probes (used by tests and bench.py; not part of the reference surface)
+ * Single-op entry points over HOST buffers so each kernel can be checked in isolation. */
+int wb_dbg_gemm(wb_ctx* ctx, int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16,
+                const float* bias, const float* residual, int gelu, float scale, int out_f16,
+                void* out);
+int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f16 /* [n_seg*T][3*H*64] */,
+                     uint16_t* out_f16 /* [n_seg*T][H*64] */);
+int wb_dbg_layernorm(wb_ctx* ctx, int rows, int d, const float* x, const float* w, const float* b,
+                     uint16_t* out_f16);
+/* device-side timing of the last call of each kind, in microseconds, per kernel family */
+int wb_kernel_time_us(const wb_ctx* ctx, const char* family, double* total_us, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

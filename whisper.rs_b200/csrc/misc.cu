@@ -1,0 +1,170 @@
+// misc.cu -- small fused kernels around the GEMMs (sm_100a, CUDA cores, HBM-bound).
+#include "ptx.cuh"
+#include "wb_kernels.hpp"
+
+namespace wb {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// E0: mel window copy (src/main.rs:1816-1829) fused with the F16 rounding ggml's conv applies to
+// its source and with the transpose to token-major rows the conv-as-GEMM reads through TMA:
+//   in  mel [clip][n_mel][n_len] f32 (time contiguous)
+//   out [seg][Tm + 2][n_mel] f16, rows 0 and Tm+1 stay zero (the conv's zero padding)
+// 32 x 32 tiles through shared memory so both the read (along time) and the write (along mel)
+// are coalesced.
+__global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
+                                  const long long* __restrict__ offsets, int Tm, __half* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int seg = blockIdx.z;
+  const int clip = clip_ids ? clip_ids[seg] : 0;
+  const long long off = offsets ? offsets[seg] : 0;
+  const float* src = mel + (size_t)clip * n_mel * n_len;
+  const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r, t = t0 + threadIdx.x;
+    const long long i = off + t;
+    float v = 0.0f;
+    if (j < n_mel && t < Tm && i < n_len) v = src[(size_t)j * n_len + i];   // zero past the clip end (1820-1828)
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  __half* dst = out + (size_t)seg * (Tm + 2) * n_mel;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int t = t0 + r, j = j0 + threadIdx.x;
+    if (t < Tm && j < n_mel) dst[(size_t)(t + 1) * n_mel + j] = __float2half_rn(tile[threadIdx.x][r]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E4: galois_norm + repeat/mul/add (src/main.rs:1781-1785, 1882-1886): one warp per row of d,
+// the row held in registers (two-pass mean / variance, eps = 1e-5, biased variance), affine,
+// F16 store = the rounding the following matmul applies to its activation operand.
+constexpr int LN_MAX_V4 = 10;   // d <= 1280
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows,
+                 int d, __half* __restrict__ out_f16, float* __restrict__ out_f32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nv4 = d >> 2;   // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * d);
+  float4 v[LN_MAX_V4];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv4) {
+      v[i] = xr[idx];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv4) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)d + 1e-5f);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv4) {
+      const float4 ww = __ldg(w4 + idx), bb = __ldg(b4 + idx);
+      float4 y;
+      y.x = ww.x * (v[i].x * rstd) + bb.x;
+      y.y = ww.y * (v[i].y * rstd) + bb.y;
+      y.z = ww.z * (v[i].z * rstd) + bb.z;
+      y.w = ww.w * (v[i].w * rstd) + bb.w;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)warp * d)[idx] = y;
+      if (out_f16) {
+        uint2 u;
+        u.x = pack_h2(y.x, y.y);
+        u.y = pack_h2(y.z, y.w);
+        reinterpret_cast<uint2*>(out_f16 + (size_t)warp * d)[idx] = u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sum|x| probes (the author's checkpoints, src/main.rs:1836-1849): one double per segment
+__global__ void abs_sum_f32_kernel(const float* __restrict__ x, long long per_seg, long long seg_stride,
+                                   double* __restrict__ out) {
+  const int seg = blockIdx.y;
+  const float* p = x + (size_t)seg * seg_stride;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_seg; i += (long long)gridDim.x * blockDim.x)
+    acc += (double)fabsf(p[i]);
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(&out[seg], sh[0]);
+}
+
+__global__ void abs_sum_f16_kernel(const __half* __restrict__ x, int rows, int cols, long long row_stride,
+                                   long long seg_stride, double* __restrict__ out) {
+  const int seg = blockIdx.y;
+  const __half* p = x + (size_t)seg * seg_stride;
+  const long long n = (long long)rows * cols;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    acc += (double)fabsf(__half2float(p[r * row_stride + c]));
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(&out[seg], sh[0]);
+}
+
+}  // namespace
+
+cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int* clip_ids, const long long* offsets,
+                              int n_seg, int Tm, __half* out, cudaStream_t st) {
+  dim3 grid((Tm + 31) / 32, (n_mel + 31) / 32, n_seg);
+  mel_window_kernel<<<grid, dim3(32, 8), 0, st>>>(mel, n_mel, n_len, clip_ids, offsets, Tm, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d, __half* out_f16,
+                             float* out_f32, cudaStream_t st) {
+  if (d % 4 != 0 || d > 128 * LN_MAX_V4) return cudaErrorInvalidValue;
+  const int warps_per_block = 8;
+  layernorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(x, w, b, rows, d,
+                                                                                                  out_f16, out_f32);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_abs_sum_f32(const float* x, long long per_seg, long long seg_stride, int n_seg, double* out,
+                               cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * n_seg, st);
+  if (e != cudaSuccess) return e;
+  abs_sum_f32_kernel<<<dim3(64, n_seg), 256, 0, st>>>(x, per_seg, seg_stride, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long row_stride, long long seg_stride,
+                               int n_seg, double* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * n_seg, st);
+  if (e != cudaSuccess) return e;
+  abs_sum_f16_kernel<<<dim3(64, n_seg), 256, 0, st>>>(x, rows, cols, row_stride, seg_stride, out);
+  return cudaGetLastError();
+}
+
+}  // namespace wb

@@ -1,0 +1,1068 @@
+// wb_api.cu -- C-ABI entry points: context creation (loader + weight upload), log-mel, encoder.
+// Mirrors the reference's call order main -> WhisperContext::new -> whisper_pcm_to_mel ->
+// whisper_encode (src/main.rs:2065-2075) behind include/whisper_b200.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "wb_internal.hpp"
+
+namespace wb {
+
+static thread_local std::string g_err;
+void set_global_error(const std::string& msg) { g_err = msg; }
+
+int fail(wb_ctx* ctx, int code, const char* what, cudaError_t e) {
+  std::string m = std::string("galois tensor:'") + what + ": " + cudaGetErrorString(e) + "'";
+  if (ctx) ctx->err = m;
+  g_err = m;
+  return code;
+}
+int fail_msg(wb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const char** err) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    *err = "cuTensorMapEncodeTiled not available (no CUDA driver?)";
+    return false;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static thread_local char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu,%llu box %u,%u)", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+             rank > 1 ? box[1] : 0);
+    *err = buf;
+    return false;
+  }
+  return true;
+}
+
+bool tmap_2d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
+                  const char** err) {
+  const uint64_t dims[2] = {K, rows};
+  const uint64_t st[1] = {ld_elems * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return make_tmap_f16(m, base, 2, dims, st, box, err);
+}
+bool tmap_3d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                  uint64_t bstride_elems, const char** err) {
+  const uint64_t dims[3] = {K, rows, batch};
+  const uint64_t st[2] = {ld_elems * 2, bstride_elems * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return make_tmap_f16(m, base, 3, dims, st, box, err);
+}
+
+bool make_linear_maps(wb_ctx* ctx, Linear& l, bool want_a_map) {
+  const char* err = "";
+  l.bn = gemm_pick_bn(l.N);
+  if (!tmap_2d_rows(&l.map_w, l.w, l.K, l.N, l.K, l.bn, &err)) {
+    fail_msg(ctx, WB_ERR_TENSOR_OP, err);
+    return false;
+  }
+  if (want_a_map) {
+    if (!tmap_3d_rows(&l.map_a, l.w, l.K, l.N, 1, l.K, (uint64_t)l.K * l.N, &err)) {
+      fail_msg(ctx, WB_ERR_TENSOR_OP, err);
+      return false;
+    }
+    l.has_map_a = true;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-family timing
+struct PendingEvent {
+  const char* fam;
+  cudaEvent_t a, b;
+};
+static std::unordered_map<wb_ctx*, std::vector<PendingEvent>> g_pending;
+static std::unordered_map<wb_ctx*, std::vector<cudaEvent_t>> g_free_events;
+
+static cudaEvent_t get_event(wb_ctx* c) {
+  auto& pool = g_free_events[c];
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+LaunchTimer::LaunchTimer(wb_ctx* ctx, const char* family) : c(ctx), fam(family) {
+  ++c->tm.n_kernel_launches;
+  if (c->time_kernels) {
+    a = get_event(c);
+    b = get_event(c);
+    cudaEventRecord(a, c->stream);
+  }
+}
+LaunchTimer::~LaunchTimer() {
+  if (a) {
+    cudaEventRecord(b, c->stream);
+    g_pending[c].push_back(PendingEvent{fam, a, b});
+  }
+}
+void resolve_kernel_clocks(wb_ctx* ctx) {
+  auto it = g_pending.find(ctx);
+  if (it == g_pending.end()) return;
+  for (auto& pe : it->second) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(pe.b) == cudaSuccess && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+      KernelClock& k = ctx->clocks[pe.fam];
+      k.total_us += (double)ms * 1000.0;
+      k.launches += 1;
+    }
+    g_free_events[ctx].push_back(pe.a);
+    g_free_events[ctx].push_back(pe.b);
+  }
+  it->second.clear();
+}
+
+int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const Linear& l, GemmEpilogue epi,
+             const char* family) {
+  GemmProblem g;
+  g.a_map = a_map;
+  g.w_map = l.map_w;
+  g.M_rows = M_rows;
+  g.batch = batch;
+  g.N = l.N;
+  g.K = l.K;
+  g.bn = l.bn;
+  if (!epi.bias) epi.bias = l.bias;
+  if (!epi.colscale) epi.colscale = l.colscale;
+  g.epi = epi;
+  LaunchTimer t(ctx, family);
+  WB_CK(launch_gemm(g, ctx->num_sms, ctx->stream));
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight upload
+const HostTensor* find(const ModelFileView& mv, const std::string& n) {
+  auto it = mv.tensors.find(n);
+  return it == mv.tensors.end() ? nullptr : &it->second;
+}
+
+// host tensor -> f16 vector (weights stored F32 in the file are rounded to F16: the tensor cores
+// take F16 operands; files with hparams.f16 == 1 pass through bit-exactly)
+void to_f16_host(const HostTensor& t, std::vector<__half>& out) {
+  const int64_t n = t.nelem();
+  out.resize((size_t)n);
+  if (t.f16) {
+    memcpy(out.data(), t.data, (size_t)n * 2);
+  } else {
+    for (int64_t i = 0; i < n; ++i) {
+      float f;
+      memcpy(&f, t.data + 4 * i, 4);
+      out[(size_t)i] = __float2half_rn(f);
+    }
+  }
+}
+
+int upload_f32(wb_ctx* ctx, const ModelFileView& mv, const std::string& name, const float** out) {
+  const HostTensor* t = find(mv, name);
+  if (!t || t->f16) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + name + "'\n");
+  float* d = nullptr;
+  int rc = dev_alloc(ctx, &d, (size_t)t->nelem(), false);
+  if (rc) return rc;
+  WB_CK(cudaMemcpyAsync(d, t->data, t->bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *out = d;
+  return WB_OK;
+}
+
+int upload_f16_vec(wb_ctx* ctx, const std::vector<__half>& h, __half** out) {
+  __half* d = nullptr;
+  int rc = dev_alloc(ctx, &d, h.size(), false);
+  if (rc) return rc;
+  WB_CK(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));   // h is a temporary: synchronous
+  *out = d;
+  return WB_OK;
+}
+int upload_f32_vec(wb_ctx* ctx, const std::vector<float>& h, const float** out) {
+  float* d = nullptr;
+  int rc = dev_alloc(ctx, &d, h.size(), false);
+  if (rc) return rc;
+  WB_CK(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  *out = d;
+  return WB_OK;
+}
+
+int upload_linear(wb_ctx* ctx, const ModelFileView& mv, const std::string& wname, const std::string& bname,
+                  Linear& l, bool want_a_map) {
+  const HostTensor* t = find(mv, wname);
+  if (!t) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + wname + "'\n");
+  std::vector<__half> h;
+  to_f16_host(*t, h);
+  l.K = (int)t->ne[0];
+  l.N = (int)t->ne[1];
+  int rc = upload_f16_vec(ctx, h, &l.w);
+  if (rc) return rc;
+  if (!bname.empty()) {
+    rc = upload_f32(ctx, mv, bname, &l.bias);
+    if (rc) return rc;
+  }
+  return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
+}
+
+// conv weight file layout [Cout][Cin][3] (ne = [3, Cin, Cout], src/main.rs:961-965) ->
+// [Cout][k][Cin] so that one GEMM row of the activation operand is the contiguous run of three
+// consecutive token-major input rows.
+int upload_conv(wb_ctx* ctx, const ModelFileView& mv, const std::string& wname, const std::string& bname,
+                Linear& l) {
+  const HostTensor* t = find(mv, wname);
+  if (!t) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + wname + "'\n");
+  std::vector<__half> h, r;
+  to_f16_host(*t, h);
+  const int Cin = (int)t->ne[1], Cout = (int)t->ne[2];
+  r.resize(h.size());
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int k = 0; k < 3; ++k) r[((size_t)co * 3 + k) * Cin + ci] = h[((size_t)co * Cin + ci) * 3 + k];
+  l.K = 3 * Cin;
+  l.N = Cout;
+  int rc = upload_f16_vec(ctx, r, &l.w);
+  if (rc) return rc;
+  rc = upload_f32(ctx, mv, bname, &l.bias);
+  if (rc) return rc;
+  return make_linear_maps(ctx, l, false) ? WB_OK : WB_ERR_TENSOR_OP;
+}
+
+// concatenate weight rows of several tensors into one [sum N][K] matrix (+ bias / column scale)
+int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, Linear& l, bool want_a_map) {
+  std::vector<__half> h;
+  std::vector<float> bias, cs;
+  bool any_scale = false;
+  int K = 0;
+  for (const CatPart& p : parts) {
+    const HostTensor* t = find(mv, p.w);
+    if (!t) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.w + "'\n");
+    std::vector<__half> part;
+    to_f16_host(*t, part);
+    K = (int)t->ne[0];
+    const int N = (int)t->ne[1];
+    h.insert(h.end(), part.begin(), part.end());
+    if (!p.b.empty()) {
+      const HostTensor* bt = find(mv, p.b);
+      if (!bt) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.b + "'\n");
+      const size_t o = bias.size();
+      bias.resize(o + N);
+      memcpy(bias.data() + o, bt->data, (size_t)N * 4);
+    } else {
+      bias.resize(bias.size() + N, 0.0f);
+    }
+    cs.resize(cs.size() + N, p.scale);
+    if (p.scale != 1.0f) any_scale = true;
+  }
+  l.K = K;
+  l.N = (int)(h.size() / (size_t)K);
+  int rc = upload_f16_vec(ctx, h, &l.w);
+  if (rc) return rc;
+  rc = upload_f32_vec(ctx, bias, &l.bias);
+  if (rc) return rc;
+  if (any_scale) {
+    rc = upload_f32_vec(ctx, cs, &l.colscale);
+    if (rc) return rc;
+  }
+  return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
+}
+
+int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
+  const int n_mel = mv.filt_n_mel;
+  if (mv.filt_n_fft != 201) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: mel filterbank must have 201 bins");
+  std::vector<float> hann(400);
+  std::vector<float2> w200(200), w400(201);
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < 400; ++i) hann[i] = (float)(0.5 * (1.0 - cos(2.0 * PI * i / 400.0)));   // periodic (1567-1569)
+  for (int i = 0; i < 200; ++i) w200[i] = make_float2((float)cos(2.0 * PI * i / 200.0), (float)-sin(2.0 * PI * i / 200.0));
+  for (int i = 0; i < 201; ++i) w400[i] = make_float2((float)cos(2.0 * PI * i / 400.0), (float)-sin(2.0 * PI * i / 400.0));
+  std::vector<float> filt((size_t)n_mel * 201);
+  memcpy(filt.data(), mv.filters, filt.size() * 4);
+  std::vector<int2> range(n_mel);
+  for (int j = 0; j < n_mel; ++j) {   // span of non-zero taps; exact zeros add nothing to the f32 sum
+    int lo = 201, hi = 0;
+    for (int k = 0; k < 201; ++k)
+      if (filt[(size_t)j * 201 + k] != 0.0f) {
+        lo = k < lo ? k : lo;
+        hi = k + 1;
+      }
+    if (lo >= hi) lo = hi = 0;
+    range[j] = make_int2(lo, hi);
+  }
+  float *d_hann, *d_filt;
+  float2 *d_w200, *d_w400;
+  int2* d_range;
+  int rc;
+  if ((rc = dev_alloc(ctx, &d_hann, 400, false))) return rc;
+  if ((rc = dev_alloc(ctx, &d_w200, 200, false))) return rc;
+  if ((rc = dev_alloc(ctx, &d_w400, 201, false))) return rc;
+  if ((rc = dev_alloc(ctx, &d_filt, filt.size(), false))) return rc;
+  if ((rc = dev_alloc(ctx, &d_range, (size_t)n_mel, false))) return rc;
+  WB_CK(cudaMemcpy(d_hann, hann.data(), 1600, cudaMemcpyHostToDevice));
+  WB_CK(cudaMemcpy(d_w200, w200.data(), 1600, cudaMemcpyHostToDevice));
+  WB_CK(cudaMemcpy(d_w400, w400.data(), 1608, cudaMemcpyHostToDevice));
+  WB_CK(cudaMemcpy(d_filt, filt.data(), filt.size() * 4, cudaMemcpyHostToDevice));
+  WB_CK(cudaMemcpy(d_range, range.data(), (size_t)n_mel * 8, cudaMemcpyHostToDevice));
+  ctx->mel_tab = MelTables{d_hann, d_w200, d_w400, d_filt, d_range, n_mel};
+  return WB_OK;
+}
+
+int alloc_activations(wb_ctx* ctx) {
+  const ModelHParams& hp = ctx->hp;
+  const size_t S = (size_t)ctx->cfg.max_segments;
+  const size_t T = hp.n_audio_ctx, Tm = 2 * T, d = hp.n_audio_state, Lt = hp.n_text_layer;
+  ctx->Tp = (int)((T + 127) / 128 * 128);
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_clip_ids, S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_offsets, S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->conv_in, S * (Tm + 2) * hp.n_mels))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->h1, S * (Tm + 2) * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->x, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->ln_out, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->qk, S * T * 2 * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->vt, S * d * ctx->Tp))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->attn_out, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->hidden, S * T * 4 * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->enc_out, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->enc_f16, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->cross, S * T * Lt * 2 * d))) return rc;
+  ctx->n_chk_slots = 4 + hp.n_audio_layer + 2 * hp.n_text_layer;
+  if ((rc = dev_alloc(ctx, &ctx->d_chk, (size_t)ctx->n_chk_slots * S))) return rc;
+  ctx->chk_valid.assign(ctx->n_chk_slots, 0);
+  // mel buffers
+  const size_t max_len = (size_t)(ctx->cfg.max_clip_samples / 160);
+  ctx->d_mel_floats = (size_t)ctx->cfg.max_clips * ctx->mel_tab.n_mel * (max_len ? max_len : 1);
+  if ((rc = dev_alloc(ctx, &ctx->d_mel, ctx->d_mel_floats))) return rc;
+  ctx->d_pcm_bytes = (size_t)ctx->cfg.max_clips * (size_t)ctx->cfg.max_clip_samples * 4;
+  uint8_t* pcm = nullptr;
+  if ((rc = dev_alloc(ctx, &pcm, ctx->d_pcm_bytes, false))) return rc;
+  ctx->d_pcm = pcm;
+  if ((rc = dev_alloc(ctx, &ctx->d_clip_max, (size_t)ctx->cfg.max_clips))) return rc;
+  return WB_OK;
+}
+
+int chk_slot(const wb_ctx* ctx, int stage, int layer) {
+  const int L = ctx->hp.n_audio_layer, Lt = ctx->hp.n_text_layer;
+  switch (stage) {
+    case WB_STAGE_MEL: return 0;
+    case WB_STAGE_CONV1: return 1;
+    case WB_STAGE_CONV2_POS: return 2;
+    case WB_STAGE_LAYER: return (layer >= 0 && layer < L) ? 3 + layer : -1;
+    case WB_STAGE_LN_POST: return 3 + L;
+    case WB_STAGE_CROSS_K: return (layer >= 0 && layer < Lt) ? 4 + L + 2 * layer : -1;
+    case WB_STAGE_CROSS_V: return (layer >= 0 && layer < Lt) ? 5 + L + 2 * layer : -1;
+    default: return -1;
+  }
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" {
+
+const char* wb_version(void) { return "whisper_b200 0.1 (sm_100a)"; }
+
+const char* wb_last_error(const wb_ctx* ctx) { return ctx ? ctx->err.c_str() : wb::g_err.c_str(); }
+
+void wb_config_default(wb_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0;
+  cfg->max_segments = 1;
+  cfg->max_clips = 1;
+  cfg->max_clip_samples = 480000;   // WHISPER_SAMPLE_RATE * WHISPER_CHUNK_SIZE (25, 29)
+  cfg->norm_scope = WB_NORM_CLIP;
+  cfg->checkpoints = 0;
+  cfg->stream = nullptr;
+  cfg->decode_capacity = 1;
+}
+
+int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out) {
+  if (!model_path || !out) return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: null argument");
+  *out = nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  wb_config cfg;
+  if (cfg_in) cfg = *cfg_in;
+  else wb_config_default(&cfg);
+  if (cfg.max_segments < 1 || cfg.max_clips < 1 || cfg.max_clip_samples < 400)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: bad wb_config capacities");
+
+  ModelFileView mv;
+  std::string perr;
+  int rc = parse_model_file(model_path, mv, perr);
+  if (rc != WB_OK) return fail_msg(nullptr, rc, perr);
+  const ModelHParams& hp = mv.hp;
+  if (hp.n_audio_state / hp.n_audio_head != 64 || hp.n_text_state / hp.n_text_head != 64)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: head dimension must be 64");
+  if (hp.n_audio_state != hp.n_text_state)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: n_audio_state != n_text_state");
+  if (hp.n_audio_state % 64 != 0 || hp.n_audio_state > 1280 || hp.n_mels % 8 != 0 || mv.filt_n_mel != hp.n_mels)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: unsupported model dimensions");
+
+  // ---- device: no CPU fallback
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail_msg(nullptr, WB_ERR_TENSOR_OP, std::string("galois tensor:'no CUDA device: ") + cudaGetErrorString(e) +
+                                                   "' (libwhisper_b200 has no CPU fallback)");
+  if (cfg.device < 0 || cfg.device >= n_dev) return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: bad device ordinal");
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(cfg.device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess)
+    return fail(nullptr, WB_ERR_TENSOR_OP, "cudaSetDevice", e);
+  if (prop.major != 10)
+    return fail_msg(nullptr, WB_ERR_TENSOR_OP, "galois tensor:'device is not sm_100 (Blackwell B200); kernels are sm_100a only'");
+
+  wb_ctx* ctx = new wb_ctx();
+  ctx->cfg = cfg;
+  ctx->device = cfg.device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->hp = hp;
+  memcpy(ctx->special, mv.special, sizeof(mv.special));
+  ctx->time_kernels = cfg.reserved[0] != 0;
+  auto bail = [&](int code) {
+    std::string m = ctx->err;
+    wb_ctx_free(ctx);
+    wb::g_err = m;
+    return code;
+  };
+  if (cfg.stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(cfg.stream);
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      fail(ctx, WB_ERR_TENSOR_OP, "cudaStreamCreate", e);
+      return bail(WB_ERR_TENSOR_OP);
+    }
+    ctx->own_stream = true;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
+  const char* aerr = "";
+  if (!gemm_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
+    fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'kernel attribute setup: ") + aerr + "'");
+    return bail(WB_ERR_TENSOR_OP);
+  }
+
+  // ---- weights (tensor table of src/main.rs:960-1334)
+#define TRY(x)            \
+  do {                    \
+    rc = (x);             \
+    if (rc) return bail(rc); \
+  } while (0)
+  TRY(build_mel_tables(ctx, mv));
+  TRY(upload_f32(ctx, mv, "encoder.positional_embedding", &ctx->e_pe));
+  TRY(upload_conv(ctx, mv, "encoder.conv1.weight", "encoder.conv1.bias", ctx->conv1));
+  TRY(upload_conv(ctx, mv, "encoder.conv2.weight", "encoder.conv2.bias", ctx->conv2));
+  TRY(upload_f32(ctx, mv, "encoder.ln_post.weight", &ctx->ln_post_w));
+  TRY(upload_f32(ctx, mv, "encoder.ln_post.bias", &ctx->ln_post_b));
+  ctx->enc.resize(hp.n_audio_layer);
+  for (int i = 0; i < hp.n_audio_layer; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    EncLayer& l = ctx->enc[i];
+    TRY(upload_f32(ctx, mv, p + "attn_ln.weight", &l.attn_ln_w));
+    TRY(upload_f32(ctx, mv, p + "attn_ln.bias", &l.attn_ln_b));
+    TRY(upload_f32(ctx, mv, p + "mlp_ln.weight", &l.mlp_ln_w));
+    TRY(upload_f32(ctx, mv, p + "mlp_ln.bias", &l.mlp_ln_b));
+    // Q (+b), K (no bias), V (+b) fused into one [3d][d] weight (1891-1897)
+    TRY(upload_cat(ctx, mv,
+                   {{p + "attn.query.weight", p + "attn.query.bias", 1.0f},
+                    {p + "attn.key.weight", "", 1.0f},
+                    {p + "attn.value.weight", p + "attn.value.bias", 1.0f}},
+                   l.qkv, false));
+    TRY(upload_linear(ctx, mv, p + "attn.out.weight", p + "attn.out.bias", l.out, false));
+    TRY(upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, false));
+    TRY(upload_linear(ctx, mv, p + "mlp.2.weight", p + "mlp.2.bias", l.fc2, false));
+  }
+  {
+    // cross-attention K/V of every text layer as one GEMM: K rows scaled by (d/H)^-1/4 with no
+    // bias (1992-1996), V rows + bias (2013-2016)
+    const float ks = powf((float)hp.n_audio_state / (float)hp.n_audio_head, -0.25f);
+    std::vector<CatPart> parts;
+    for (int i = 0; i < hp.n_text_layer; ++i) {
+      const std::string p = "decoder.blocks." + std::to_string(i) + ".cross_attn.";
+      parts.push_back({p + "key.weight", "", ks});
+      parts.push_back({p + "value.weight", p + "value.bias", 1.0f});
+    }
+    if (!parts.empty()) TRY(upload_cat(ctx, mv, parts, ctx->cross_kv, false));
+  }
+  TRY(alloc_activations(ctx));
+  if (cfg.decode_capacity) TRY(decode_setup(ctx, mv));   // decoder weights + KV cache (wb_decode.cu)
+#undef TRY
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    fail(ctx, WB_ERR_TENSOR_OP, "weight upload", e);
+    return bail(WB_ERR_TENSOR_OP);
+  }
+  ctx->tm.t_load_us =
+      std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
+  *out = ctx;
+  return WB_OK;
+}
+
+void wb_ctx_free(wb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  resolve_kernel_clocks(ctx);
+  for (cudaEvent_t e : wb::g_free_events[ctx]) cudaEventDestroy(e);
+  wb::g_free_events.erase(ctx);
+  wb::g_pending.erase(ctx);
+  for (void* p : ctx->allocs) cudaFree(p);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int wb_get_hparams(const wb_ctx* ctx, int32_t out[11]) {
+  if (!ctx || !out) return WB_ERR_UNEXPECTED;
+  memcpy(out, &ctx->hp, 44);
+  return WB_OK;
+}
+int wb_get_special_tokens(const wb_ctx* ctx, int32_t out[8]) {
+  if (!ctx || !out) return WB_ERR_UNEXPECTED;
+  memcpy(out, ctx->special, 32);
+  return WB_OK;
+}
+
+int wb_sync(wb_ctx* ctx) {
+  if (!ctx) return WB_ERR_UNEXPECTED;
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whisper_pcm_to_mel (src/main.rs:1681-1707)
+static int mel_run(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_samples, int n_clips) {
+  const int n_mel = ctx->mel_tab.n_mel;
+  const size_t n_len = n_samples / 160;   // 1575
+  if (n_clips < 1 || n_clips > ctx->cfg.max_clips || (size_t)n_clips * n_mel * n_len > ctx->d_mel_floats)
+    return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  cudaEventRecord(ctx->ev[0][0], ctx->stream);
+  {
+    LaunchTimer t(ctx, "fill");
+    WB_CK(launch_fill_i32(ctx->d_clip_max, n_clips, mel_enc_ordered_host(-1e20f), ctx->stream));   // mmax = -1e20 (1655)
+  }
+  {
+    LaunchTimer t(ctx, "mel_frames");
+    WB_CK(launch_mel_frames(ctx->mel_tab, pcm_dev, is_i16, n_samples, n_clips, (int)n_len, ctx->d_mel, ctx->d_clip_max,
+                            ctx->stream));
+  }
+  {
+    LaunchTimer t(ctx, "mel_normalize");
+    WB_CK(launch_mel_normalize(ctx->d_mel, n_clips, (size_t)n_mel * n_len, ctx->d_clip_max, ctx->stream));
+  }
+  ctx->mel_n_len = (int)n_len;
+  ctx->mel_n_clips = n_clips;
+  if (ctx->cfg.checkpoints) {
+    WB_CK(launch_abs_sum_f32(ctx->d_mel, (long long)n_mel * n_len, (long long)n_mel * n_len,
+                             n_clips < ctx->cfg.max_segments ? n_clips : ctx->cfg.max_segments, ctx->d_chk, ctx->stream));
+    ctx->chk_valid[0] = 1;
+  }
+  cudaEventRecord(ctx->ev[0][1], ctx->stream);
+  ctx->ev_used[0] = true;
+  ctx->tm.n_mel_calls += 1;
+  return WB_OK;
+}
+
+int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, int n_clips) {
+  if (!ctx || !pcm_dev) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  return mel_run(ctx, pcm_dev, 0, n_samples, n_clips);
+}
+
+int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips) {
+  if (!ctx || !pcm) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)n_clips * n_samples * 4;
+  if (n_clips < 1 || bytes > ctx->d_pcm_bytes)
+    return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  WB_CK(cudaMemcpyAsync(ctx->d_pcm, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return mel_run(ctx, ctx->d_pcm, 0, n_samples, n_clips);
+}
+
+int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_clips) {
+  if (!ctx || !pcm) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)n_clips * n_samples * 2;
+  if (n_clips < 1 || bytes > ctx->d_pcm_bytes)
+    return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  WB_CK(cudaMemcpyAsync(ctx->d_pcm, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return mel_run(ctx, ctx->d_pcm, 1, n_samples, n_clips);
+}
+
+int wb_mel_dims(const wb_ctx* ctx, int* n_mel, int* n_len, int* n_clips) {
+  if (!ctx) return WB_ERR_UNEXPECTED;
+  if (n_mel) *n_mel = ctx->mel_tab.n_mel;
+  if (n_len) *n_len = ctx->mel_n_len;
+  if (n_clips) *n_clips = ctx->mel_n_clips;
+  return WB_OK;
+}
+
+int wb_mel_read(wb_ctx* ctx, int clip, float* out, size_t cap_floats) {
+  if (!ctx || !out || clip < 0 || clip >= ctx->mel_n_clips) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->mel_tab.n_mel * ctx->mel_n_len;
+  if (cap_floats < n) return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  WB_CK(cudaMemcpyAsync(out, ctx->d_mel + (size_t)clip * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clips) {
+  if (!ctx || !mel || n_mel != ctx->mel_tab.n_mel || n_clips < 1 || n_clips > ctx->cfg.max_clips) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)n_clips * n_mel * n_len;
+  if (n > ctx->d_mel_floats) return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  WB_CK(cudaMemcpyAsync(ctx->d_mel, mel, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  ctx->mel_n_len = n_len;
+  ctx->mel_n_clips = n_clips;
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whisper_encode (src/main.rs:1799-2063), batched over segments
+int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, int n_seg) {
+  if (!ctx) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const ModelHParams& hp = ctx->hp;
+  if (n_seg < 1 || n_seg > ctx->cfg.max_segments)
+    return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  if (ctx->mel_n_clips < 1 || ctx->mel_tab.n_mel != hp.n_mels)   // assert 1813
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: no mel in the context (call wb_pcm_to_mel first)");
+  const int T = hp.n_audio_ctx, Tm = 2 * T, d = hp.n_audio_state, H = hp.n_audio_head, L = hp.n_audio_layer;
+  const int Lt = hp.n_text_layer, n_mels = hp.n_mels;
+  const int M = n_seg * T;
+  const bool chk = ctx->cfg.checkpoints != 0;
+  cudaStream_t st = ctx->stream;
+  const char* terr = "";
+
+  // segment table
+  std::vector<int> ids(n_seg, 0);
+  std::vector<long long> offs(n_seg, 0);
+  for (int s = 0; s < n_seg; ++s) {
+    if (clip_ids) ids[s] = clip_ids[s];
+    if (mel_offsets) offs[s] = (long long)mel_offsets[s];
+    if (ids[s] < 0 || ids[s] >= ctx->mel_n_clips) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: clip id out of range");
+  }
+  cudaEventRecord(ctx->ev[1][0], st);
+  WB_CK(cudaMemcpyAsync(ctx->d_clip_ids, ids.data(), sizeof(int) * n_seg, cudaMemcpyHostToDevice, st));
+  WB_CK(cudaMemcpyAsync(ctx->d_offsets, offs.data(), sizeof(long long) * n_seg, cudaMemcpyHostToDevice, st));
+  WB_CK(cudaStreamSynchronize(st));   // ids/offs are stack temporaries (tiny copy)
+
+  // ---- tensor maps of the activation operands for this batch size
+  CUtensorMap m_conv1, m_conv2, m_ln, m_att, m_hid, m_enc;
+  AttnProblem ap;
+  bool ok = tmap_3d_rows(&m_conv1, ctx->conv_in, 3 * n_mels, Tm, n_seg, n_mels, (uint64_t)(Tm + 2) * n_mels, &terr) &&
+            tmap_3d_rows(&m_conv2, ctx->h1, 3 * d, T, n_seg, 2 * d, (uint64_t)(Tm + 2) * d, &terr) &&
+            tmap_3d_rows(&m_ln, ctx->ln_out, d, M, 1, d, (uint64_t)M * d, &terr) &&
+            tmap_3d_rows(&m_att, ctx->attn_out, d, M, 1, d, (uint64_t)M * d, &terr) &&
+            tmap_3d_rows(&m_hid, ctx->hidden, 4 * d, M, 1, 4 * d, (uint64_t)M * 4 * d, &terr) &&
+            tmap_3d_rows(&m_enc, ctx->enc_f16, d, M, 1, d, (uint64_t)M * d, &terr);
+  if (ok) {
+    // Q|K buffer [seg*T][2d] viewed as {64, 2H, T, seg}
+    const uint64_t dims[4] = {64, (uint64_t)2 * H, (uint64_t)T, (uint64_t)n_seg};
+    const uint64_t strd[3] = {128, (uint64_t)2 * d * 2, (uint64_t)T * 2 * d * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    ok = make_tmap_f16(&ap.qk_map, ctx->qk, 4, dims, strd, box, &terr);
+  }
+  if (ok) {
+    const uint64_t dims[2] = {(uint64_t)ctx->Tp, (uint64_t)n_seg * d};
+    const uint64_t strd[1] = {(uint64_t)ctx->Tp * 2};
+    const uint32_t box[2] = {64, 64};
+    ok = make_tmap_f16(&ap.vt_map, ctx->vt, 2, dims, strd, box, &terr);
+  }
+  if (!ok) return fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
+  ap.B = n_seg;
+  ap.T = T;
+  ap.H = H;
+  ap.out = ctx->attn_out;
+  ap.scale = 1.0f / sqrtf(64.0f);
+
+  auto probe_f32 = [&](int slot, const float* p, long long per_seg, long long seg_stride) -> int {
+    WB_CK(launch_abs_sum_f32(p, per_seg, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, st));
+    ctx->chk_valid[slot] = 1;
+    return WB_OK;
+  };
+  auto probe_f16 = [&](int slot, const __half* p, int rows, int cols, long long row_stride, long long seg_stride) -> int {
+    WB_CK(launch_abs_sum_f16(p, rows, cols, row_stride, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, st));
+    ctx->chk_valid[slot] = 1;
+    return WB_OK;
+  };
+  int rc;
+
+  // E0: mel window -> token-major F16 rows with zero padding rows (1816-1829)
+  {
+    LaunchTimer t(ctx, "mel_window");
+    WB_CK(launch_mel_window(ctx->d_mel, n_mels, ctx->mel_n_len, ctx->d_clip_ids, ctx->d_offsets, n_seg, Tm, ctx->conv_in, st));
+  }
+  // E1: conv1 + bias + GELU (1834-1855) as an implicit GEMM: row t = input rows t-1, t, t+1
+  {
+    GemmEpilogue e;
+    e.gelu = 1;
+    e.out = ctx->h1 + d;   // skip the leading zero row
+    e.out_f16 = 1;
+    e.out_bstride = (long long)(Tm + 2) * d;
+    e.out_ld = d;
+    if ((rc = run_gemm(ctx, m_conv1, Tm, n_seg, ctx->conv1, e, "gemm_conv"))) return rc;
+    if (chk && (rc = probe_f16(1, ctx->h1 + d, Tm, d, d, (long long)(Tm + 2) * d))) return rc;
+  }
+  // E2 + E3: conv2 (stride 2) + bias + GELU, + positional embedding (1856-1875) -> residual stream
+  {
+    GemmEpilogue e;
+    e.gelu = 1;
+    e.residual = ctx->e_pe;
+    e.res_bstride = 0;
+    e.res_ld = d;
+    e.out = ctx->x;
+    e.out_f16 = 0;
+    e.out_bstride = (long long)T * d;
+    e.out_ld = d;
+    if ((rc = run_gemm(ctx, m_conv2, T, n_seg, ctx->conv2, e, "gemm_conv"))) return rc;
+    if (chk && (rc = probe_f32(2, ctx->x, (long long)T * d, (long long)T * d))) return rc;
+  }
+  for (int il = 0; il < L; ++il) {   // 1877-1975
+    const EncLayer& l = ctx->enc[il];
+    {   // E4: attn_ln
+      LaunchTimer t(ctx, "layernorm");
+      WB_CK(launch_layernorm(ctx->x, l.attn_ln_w, l.attn_ln_b, M, d, ctx->ln_out, nullptr, st));
+    }
+    {   // E5 + E6: fused Q|K|V projection, F16 repack; V transposed, time contiguous (1891-1920)
+      GemmEpilogue e;
+      e.out = ctx->qk;
+      e.out_f16 = 1;
+      e.out_ld = 2 * d;
+      e.vt_out = ctx->vt;
+      e.vt_col0 = 2 * d;
+      e.vt_rows = d;
+      e.vt_ld = ctx->Tp;
+      e.vt_T = T;
+      if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e))) return rc;
+    }
+    {   // E7: flash attention + head merge (1922-1929)
+      LaunchTimer t(ctx, "attention");
+      WB_CK(launch_attention(ap, st));
+    }
+    {   // E8: output projection + bias + residual (1936-1942), in place on the residual stream
+      GemmEpilogue e;
+      e.residual = ctx->x;
+      e.res_ld = d;
+      e.out = ctx->x;
+      e.out_f16 = 0;
+      e.out_ld = d;
+      if ((rc = run_gemm(ctx, m_att, M, 1, l.out, e))) return rc;
+    }
+    {   // E9: mlp_ln, fc1 + bias + GELU, fc2 + bias + residual (1948-1968)
+      LaunchTimer t(ctx, "layernorm");
+      WB_CK(launch_layernorm(ctx->x, l.mlp_ln_w, l.mlp_ln_b, M, d, ctx->ln_out, nullptr, st));
+    }
+    {
+      GemmEpilogue e;
+      e.gelu = 1;
+      e.out = ctx->hidden;
+      e.out_f16 = 1;
+      e.out_ld = 4 * d;
+      if ((rc = run_gemm(ctx, m_ln, M, 1, l.fc1, e))) return rc;
+    }
+    {
+      GemmEpilogue e;
+      e.residual = ctx->x;
+      e.res_ld = d;
+      e.out = ctx->x;
+      e.out_f16 = 0;
+      e.out_ld = d;
+      if ((rc = run_gemm(ctx, m_hid, M, 1, l.fc2, e))) return rc;
+    }
+    if (chk && (rc = probe_f32(3 + il, ctx->x, (long long)T * d, (long long)T * d))) return rc;
+  }
+  {   // E11: ln_post (1980-1984): f32 copy for read-back, F16 copy as the cross-KV GEMM operand
+    LaunchTimer t(ctx, "layernorm");
+    WB_CK(launch_layernorm(ctx->x, ctx->ln_post_w, ctx->ln_post_b, M, d, ctx->enc_f16, ctx->enc_out, st));
+  }
+  if (chk && (rc = probe_f32(3 + L, ctx->enc_out, (long long)T * d, (long long)T * d))) return rc;
+  if (Lt > 0) {   // E12: cross-attention K/V of all text layers in one GEMM (1990-2030)
+    GemmEpilogue e;
+    e.out = ctx->cross;
+    e.out_f16 = 1;
+    e.out_ld = Lt * 2 * d;
+    if ((rc = run_gemm(ctx, m_enc, M, 1, ctx->cross_kv, e, "gemm_cross"))) return rc;
+    if (chk) {
+      const long long ld = (long long)Lt * 2 * d;
+      for (int il = 0; il < Lt; ++il) {
+        if ((rc = probe_f16(4 + L + 2 * il, ctx->cross + (size_t)il * 2 * d, T, d, ld, (long long)T * ld))) return rc;
+        if ((rc = probe_f16(5 + L + 2 * il, ctx->cross + (size_t)il * 2 * d + d, T, d, ld, (long long)T * ld))) return rc;
+      }
+    }
+  }
+  cudaEventRecord(ctx->ev[1][1], st);
+  ctx->ev_used[1] = true;
+  ctx->enc_n_seg = n_seg;
+  ctx->tm.n_encode_calls += 1;
+  return WB_OK;
+}
+
+int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out) {
+  if (!ctx || !out || seg < 0 || seg >= ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  WB_CK(cudaMemcpyAsync(out, ctx->enc_out + (size_t)seg * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v) {
+  if (!ctx || seg < 0 || seg >= ctx->enc_n_seg || layer < 0 || layer >= ctx->hp.n_text_layer) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const int T = ctx->hp.n_audio_ctx, d = ctx->hp.n_audio_state, Lt = ctx->hp.n_text_layer;
+  const size_t ld = (size_t)Lt * 2 * d;
+  const __half* base = ctx->cross + (size_t)seg * T * ld + (size_t)layer * 2 * d;
+  // strided device rows -> the reference's dense [n_ctx][d] slice of memory_cross_k/v (2018-2030)
+  if (k) WB_CK(cudaMemcpy2DAsync(k, (size_t)d * 2, base, ld * 2, (size_t)d * 2, T, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) WB_CK(cudaMemcpy2DAsync(v, (size_t)d * 2, base + d, ld * 2, (size_t)d * 2, T, cudaMemcpyDeviceToHost, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum) {
+  if (!ctx || !abs_sum) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const int slot = chk_slot(ctx, stage, layer);
+  if (!ctx->cfg.checkpoints || slot < 0 || !ctx->chk_valid[slot] || seg < 0 || seg >= ctx->cfg.max_segments)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: checkpoint not recorded (wb_config.checkpoints = 1?)");
+  WB_CK(cudaMemcpyAsync(abs_sum, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments + seg, 8, cudaMemcpyDeviceToHost,
+                        ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+int wb_timings_get(const wb_ctx* ctx_c, wb_timings* out) {
+  wb_ctx* ctx = const_cast<wb_ctx*>(ctx_c);
+  if (!ctx || !out) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  // each event pair brackets the most recent call of its kind (device time on the handle's stream)
+  int64_t* slots[3] = {&ctx->tm.t_mel_us, &ctx->tm.t_encode_us, &ctx->tm.t_decode_us};
+  for (int i = 0; i < 3; ++i) {
+    if (!ctx->ev_used[i]) continue;
+    float ms = 0.0f;
+    if (cudaEventSynchronize(ctx->ev[i][1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) == cudaSuccess)
+      *slots[i] = (int64_t)(ms * 1000.0f);
+  }
+  *out = ctx->tm;
+  return WB_OK;
+}
+
+int wb_kernel_time_us(const wb_ctx* ctx_c, const char* family, double* total_us, int64_t* launches) {
+  wb_ctx* ctx = const_cast<wb_ctx*>(ctx_c);
+  if (!ctx || !family) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  if (strcmp(family, "__enable__") == 0) {
+    ctx->time_kernels = true;
+    return WB_OK;
+  }
+  if (strcmp(family, "__disable__") == 0) {
+    ctx->time_kernels = false;
+    return WB_OK;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  resolve_kernel_clocks(ctx);
+  if (strcmp(family, "__reset__") == 0) {
+    ctx->clocks.clear();
+    ctx->tm.n_kernel_launches = 0;
+    return WB_OK;
+  }
+  double tot = 0;
+  int64_t n = 0;
+  const size_t flen = strlen(family);
+  for (auto& kv : ctx->clocks) {
+    if (kv.first.compare(0, flen, family) == 0) {   // prefix match: "gemm" covers gemm, gemm_conv, gemm_cross
+      tot += kv.second.total_us;
+      n += kv.second.launches;
+    }
+  }
+  if (total_us) *total_us = tot;
+  if (launches) *launches = n;
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-op probes over host buffers
+int wb_dbg_gemm(wb_ctx* ctx, int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16, const float* bias,
+                const float* residual, int gelu, float scale, int out_f16, void* out) {
+  if (!ctx || !a_f16 || !w_f16 || !out || M < 1 || N < 1 || K < 8 || K % 8 != 0) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  __half *dA = nullptr, *dW = nullptr;
+  float *dB = nullptr, *dR = nullptr;
+  void* dO = nullptr;
+  const size_t osz = (size_t)M * N * (out_f16 ? 2 : 4);
+  int rc = WB_OK;
+  const char* terr = "";
+  cudaError_t e;
+  auto cleanup = [&]() {
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dR); cudaFree(dO);
+  };
+#define DBG_CK(x)                                         \
+  do {                                                    \
+    e = (x);                                              \
+    if (e != cudaSuccess) {                               \
+      rc = fail(ctx, WB_ERR_TENSOR_OP, #x, e);            \
+      cleanup();                                          \
+      return rc;                                          \
+    }                                                     \
+  } while (0)
+  DBG_CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  DBG_CK(cudaMalloc(&dW, (size_t)N * K * 2));
+  DBG_CK(cudaMalloc(&dO, osz));
+  DBG_CK(cudaMemcpy(dA, a_f16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemcpy(dW, w_f16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemset(dO, 0, osz));
+  if (bias) {
+    DBG_CK(cudaMalloc(&dB, (size_t)N * 4));
+    DBG_CK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  }
+  if (residual) {
+    DBG_CK(cudaMalloc(&dR, (size_t)M * N * 4));
+    DBG_CK(cudaMemcpy(dR, residual, (size_t)M * N * 4, cudaMemcpyHostToDevice));
+  }
+  Linear l;
+  l.w = dW;
+  l.N = N;
+  l.K = K;
+  l.bias = dB;
+  CUtensorMap ma;
+  if (!make_linear_maps(ctx, l, false) || !tmap_3d_rows(&ma, dA, K, M, 1, K, (uint64_t)M * K, &terr)) {
+    if (*terr) fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
+    cleanup();
+    return WB_ERR_TENSOR_OP;
+  }
+  GemmEpilogue ep;
+  ep.gelu = gelu;
+  ep.scale = scale;
+  ep.residual = dR;
+  ep.res_ld = N;
+  ep.out = dO;
+  ep.out_f16 = out_f16;
+  ep.out_ld = N;
+  rc = run_gemm(ctx, ma, M, 1, l, ep, "dbg_gemm");
+  if (rc == WB_OK) {
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, WB_ERR_TENSOR_OP, "gemm kernel", e);
+  }
+  if (rc == WB_OK) DBG_CK(cudaMemcpy(out, dO, osz, cudaMemcpyDeviceToHost));
+  cleanup();
+  return rc;
+}
+
+int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f16, uint16_t* out_f16) {
+  if (!ctx || !qkv_f16 || !out_f16 || n_seg < 1 || T < 1 || H < 1) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const int d = H * 64, Tp = (T + 127) / 128 * 128;
+  const size_t M = (size_t)n_seg * T;
+  __half *dQK = nullptr, *dVt = nullptr, *dO = nullptr;
+  int rc = WB_OK;
+  cudaError_t e;
+  const char* terr = "";
+  auto cleanup = [&]() { cudaFree(dQK); cudaFree(dVt); cudaFree(dO); };
+  // host repack: Q|K rows [M][2d]; V^T [seg][d][Tp]
+  std::vector<uint16_t> qk(M * 2 * d), vt((size_t)n_seg * d * Tp, 0);
+  for (size_t m = 0; m < M; ++m) {
+    memcpy(&qk[m * 2 * d], &qkv_f16[m * 3 * d], (size_t)2 * d * 2);
+    const size_t seg = m / T, t = m % T;
+    for (int c = 0; c < d; ++c) vt[(seg * d + c) * Tp + t] = qkv_f16[m * 3 * d + 2 * d + c];
+  }
+  DBG_CK(cudaMalloc(&dQK, qk.size() * 2));
+  DBG_CK(cudaMalloc(&dVt, vt.size() * 2));
+  DBG_CK(cudaMalloc(&dO, M * d * 2));
+  DBG_CK(cudaMemcpy(dQK, qk.data(), qk.size() * 2, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemcpy(dVt, vt.data(), vt.size() * 2, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemset(dO, 0, M * d * 2));
+  AttnProblem ap;
+  {
+    const uint64_t dims[4] = {64, (uint64_t)2 * H, (uint64_t)T, (uint64_t)n_seg};
+    const uint64_t strd[3] = {128, (uint64_t)2 * d * 2, (uint64_t)T * 2 * d * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    const uint64_t dims2[2] = {(uint64_t)Tp, (uint64_t)n_seg * d};
+    const uint64_t strd2[1] = {(uint64_t)Tp * 2};
+    const uint32_t box2[2] = {64, 64};
+    if (!make_tmap_f16(&ap.qk_map, dQK, 4, dims, strd, box, &terr) ||
+        !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr)) {
+      fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
+      cleanup();
+      return WB_ERR_TENSOR_OP;
+    }
+  }
+  ap.B = n_seg;
+  ap.T = T;
+  ap.H = H;
+  ap.out = dO;
+  ap.scale = 0.125f;
+  {
+    LaunchTimer t(ctx, "dbg_attention");
+    DBG_CK(launch_attention(ap, ctx->stream));
+  }
+  DBG_CK(cudaStreamSynchronize(ctx->stream));
+  DBG_CK(cudaMemcpy(out_f16, dO, M * d * 2, cudaMemcpyDeviceToHost));
+  cleanup();
+  return rc;
+}
+
+int wb_dbg_layernorm(wb_ctx* ctx, int rows, int d, const float* x, const float* w, const float* b, uint16_t* out_f16) {
+  if (!ctx || !x || !w || !b || !out_f16) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  float *dx = nullptr, *dw = nullptr, *db = nullptr;
+  __half* dO = nullptr;
+  int rc = WB_OK;
+  cudaError_t e;
+  auto cleanup = [&]() { cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dO); };
+  DBG_CK(cudaMalloc(&dx, (size_t)rows * d * 4));
+  DBG_CK(cudaMalloc(&dw, (size_t)d * 4));
+  DBG_CK(cudaMalloc(&db, (size_t)d * 4));
+  DBG_CK(cudaMalloc(&dO, (size_t)rows * d * 2));
+  DBG_CK(cudaMemcpy(dx, x, (size_t)rows * d * 4, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemcpy(dw, w, (size_t)d * 4, cudaMemcpyHostToDevice));
+  DBG_CK(cudaMemcpy(db, b, (size_t)d * 4, cudaMemcpyHostToDevice));
+  DBG_CK(launch_layernorm(dx, dw, db, rows, d, dO, nullptr, ctx->stream));
+  DBG_CK(cudaStreamSynchronize(ctx->stream));
+  DBG_CK(cudaMemcpy(out_f16, dO, (size_t)rows * d * 2, cudaMemcpyDeviceToHost));
+  cleanup();
+  return rc;
+}
+#undef DBG_CK
+
+}  // extern "C"

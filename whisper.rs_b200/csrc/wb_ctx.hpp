@@ -1,0 +1,111 @@
+// wb_ctx.hpp -- the context behind the C-ABI handle (the reference's WhisperContext,
+// src/main.rs:333-363, re-laid-out for one B200: weights, activations and KV caches live in HBM,
+// sized from hparams instead of the MEM_REQ_* tables).
+#pragma once
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "wb_kernels.hpp"
+#include "wb_loader.hpp"
+
+namespace wb {
+
+struct Linear {            // one weight matrix [N][K] f16 (row-major, K contiguous) on the device
+  __half* w = nullptr;
+  int N = 0, K = 0;
+  int bn = 0;
+  CUtensorMap map_w;       // as the GEMM's W operand: dims {K, N}, box {64, bn}
+  CUtensorMap map_a;       // as the A operand (swap-AB decode GEMMs): dims {K, N, 1}, box {64, 128, 1}
+  bool has_map_a = false;
+  const float* bias = nullptr;
+  const float* colscale = nullptr;
+};
+
+struct EncLayer {
+  const float *attn_ln_w, *attn_ln_b, *mlp_ln_w, *mlp_ln_b;
+  Linear qkv, out, fc1, fc2;
+};
+struct DecLayer {
+  const float *attn_ln_w, *attn_ln_b, *cross_ln_w, *cross_ln_b, *mlp_ln_w, *mlp_ln_b;
+  Linear qkv, out, cq, cout, fc1, fc2;
+};
+
+struct KernelClock {   // device time per kernel family (CUDA events on the handle's stream)
+  double total_us = 0;
+  int64_t launches = 0;
+};
+
+}  // namespace wb
+
+struct wb_ctx {
+  wb_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  wb::ModelHParams hp{};
+  int32_t special[8]{};
+  std::vector<void*> allocs;
+
+  // ---- weights
+  const float* e_pe = nullptr;
+  wb::Linear conv1, conv2;            // rearranged [Cout][k][Cin]
+  const float *ln_post_w = nullptr, *ln_post_b = nullptr;
+  std::vector<wb::EncLayer> enc;
+  wb::Linear cross_kv;                // all text layers: N = Lt * 2 * d
+  const __half* d_te = nullptr;       // [n_vocab][d]
+  wb::Linear logits_lin;              // d_te as a Linear (swap-AB A operand)
+  const float *d_pe = nullptr, *d_ln_w = nullptr, *d_ln_b = nullptr;
+  std::vector<wb::DecLayer> dec;
+
+  // ---- mel
+  wb::MelTables mel_tab{};
+  void* d_pcm = nullptr;              // staging for host PCM
+  size_t d_pcm_bytes = 0;
+  float* d_mel = nullptr;             // [clip][n_mel][n_len]
+  size_t d_mel_floats = 0;
+  int* d_clip_max = nullptr;
+  int mel_n_len = 0, mel_n_clips = 0;
+
+  // ---- encoder activations (capacity = cfg.max_segments)
+  int* d_clip_ids = nullptr;
+  long long* d_offsets = nullptr;
+  __half* conv_in = nullptr;          // [seg][Tm+2][n_mel]
+  __half* h1 = nullptr;               // [seg][Tm+2][d]
+  float* x = nullptr;                 // residual stream [seg*T][d] f32
+  __half* ln_out = nullptr;           // [seg*T][d]
+  __half* qk = nullptr;               // [seg*T][2d]
+  __half* vt = nullptr;               // [seg][H*64][Tp]
+  __half* attn_out = nullptr;         // [seg*T][d]
+  __half* hidden = nullptr;           // [seg*T][4d]
+  float* enc_out = nullptr;           // [seg*T][d] f32 (ln_post)
+  __half* enc_f16 = nullptr;
+  __half* cross = nullptr;            // [seg*T][Lt*2*d]  (memory_cross_k/v)
+  int Tp = 0;
+  int enc_n_seg = 0;                  // segments of the last wb_encode
+  double* d_chk = nullptr;            // [slot][max_segments]
+  int n_chk_slots = 0;
+  std::vector<char> chk_valid;
+
+  // ---- decoder state
+  __half *self_k = nullptr, *self_v = nullptr;   // [layer][seq][n_text_ctx][d]  (memory_k/v)
+  float* dx = nullptr;                           // residual [seq*n_tok][d]
+  __half *d_ln = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_hid = nullptr, *d_q = nullptr;
+  float* d_logits = nullptr;                     // [seq][n_vocab]
+  int* d_tokens = nullptr;
+  int *d_next = nullptr, *d_out_tokens = nullptr, *d_done = nullptr, *d_out_len = nullptr;
+  float* d_margin = nullptr;
+  float *d_part_o = nullptr, *d_part_ml = nullptr;
+  int dec_max_tok = 0;
+  int dec_n_seq = 0;
+
+  // ---- timing
+  cudaEvent_t ev[3][2] = {};          // [mel|encode|decode][start|stop] of the most recent call
+  bool ev_used[3] = {false, false, false};
+  wb_timings tm{};
+  std::unordered_map<std::string, wb::KernelClock> clocks;
+  bool time_kernels = false;
+};

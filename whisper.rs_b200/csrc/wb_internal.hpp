@@ -1,0 +1,74 @@
+// wb_internal.hpp -- helpers shared by the C-ABI translation units.
+#pragma once
+
+#include <stdarg.h>
+
+#include "wb_ctx.hpp"
+
+namespace wb {
+
+int fail(wb_ctx* ctx, int code, const char* what, cudaError_t e);
+int fail_msg(wb_ctx* ctx, int code, const std::string& msg);
+void set_global_error(const std::string& msg);
+
+#define WB_CK(expr)                                                         \
+  do {                                                                      \
+    cudaError_t e_ = (expr);                                                \
+    if (e_ != cudaSuccess) return wb::fail(ctx, WB_ERR_TENSOR_OP, #expr, e_); \
+  } while (0)
+
+template <class T>
+int dev_alloc(wb_ctx* ctx, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(ctx, WB_ERR_NOT_ENOUGH_SPACE, "cudaMalloc", e);
+  if (zero) {
+    e = cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaMemset", e);
+  }
+  ctx->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return WB_OK;
+}
+
+// kernel-family device timing: event pairs recorded around launches when ctx->time_kernels
+struct LaunchTimer {
+  wb_ctx* c;
+  const char* fam;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchTimer(wb_ctx* ctx, const char* family);
+  ~LaunchTimer();
+};
+void resolve_kernel_clocks(wb_ctx* ctx);
+
+bool make_linear_maps(wb_ctx* ctx, Linear& l, bool want_a_map);
+bool tmap_2d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
+                  const char** err);
+bool tmap_3d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                  uint64_t bstride_elems, const char** err);
+
+// run one Linear as C = A * W^T with the given A map / epilogue
+int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const Linear& l, GemmEpilogue epi,
+             const char* family = "gemm");
+
+// weight upload helpers (wb_api.cu)
+const HostTensor* find(const ModelFileView& mv, const std::string& n);
+void to_f16_host(const HostTensor& t, std::vector<__half>& out);
+int upload_f32(wb_ctx* ctx, const ModelFileView& mv, const std::string& name, const float** out);
+int upload_f16_vec(wb_ctx* ctx, const std::vector<__half>& h, __half** out);
+int upload_f32_vec(wb_ctx* ctx, const std::vector<float>& h, const float** out);
+int upload_linear(wb_ctx* ctx, const ModelFileView& mv, const std::string& wname, const std::string& bname, Linear& l,
+                  bool want_a_map);
+struct CatPart {
+  std::string w, b;   // b may be empty (no bias, e.g. the key projections: src/main.rs:675, 704, 718)
+  float scale;
+};
+int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, Linear& l, bool want_a_map);
+
+int decode_setup(wb_ctx* ctx, const ModelFileView& mv);   // wb_decode.cu: decoder weights + KV cache
+
+int mel_enc_ordered_host(float f);
+float mel_dec_ordered_host(int i);
+
+}  // namespace wb

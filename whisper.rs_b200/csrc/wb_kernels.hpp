@@ -1,0 +1,112 @@
+// wb_kernels.hpp -- host-side launch interface of the hand-written sm_100a kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wb {
+
+// ---- TMA descriptors (cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint so the
+// library has no link-time dependency on libcuda) ------------------------------------------------
+// f16 tensor, up to 4 dims; dims[0] innermost (contiguous); strides_bytes[i] = stride of dim i+1.
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, const char** err);
+
+// ---- GEMM: C[b][m][n] = epi( sum_k A[b][m][k] * W[n][k] ), f16 x f16 -> f32 (TMEM) -------------
+// Restates galois_matmul (src/main.rs:1752-1767) / galois_conv_1d_* (1709-1721) call sites with
+// their bias / scale / GELU / residual / F16-repack followers fused into the epilogue.
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N] added to the accumulator
+  const float* colscale = nullptr;  // [N] multiplies (acc + bias)
+  float scale = 1.0f;               // scalar multiplier after bias (cross-K (d/H)^-1/4, 1994-1996)
+  int gelu = 0;                     // GELU (1775-1779), F16-rounded input
+  const float* residual = nullptr;  // f32 [b*res_bstride + m*res_ld + n], added last
+  long long res_bstride = 0;
+  int res_ld = 0;
+  void* out = nullptr;              // [b*out_bstride + m*out_ld + n]
+  int out_f16 = 1;
+  long long out_bstride = 0;
+  int out_ld = 0;
+  // columns n >= vt_col0 are written transposed (time contiguous) as F16:
+  //   vt_out[(seg*vt_rows + (n - vt_col0)) * vt_ld + t],  seg = m / vt_T, t = m % vt_T
+  // which is the reference's V layout `[T, Dh, H]` per segment (1914-1920).
+  __half* vt_out = nullptr;
+  int vt_col0 = 1 << 30;
+  int vt_rows = 0;
+  int vt_ld = 0;
+  int vt_T = 1;
+  // swap-AB mode for skinny activations (decoder): the GEMM computes C^T; element (m, n) is
+  // stored at out[n*out_ld + m] and bias/colscale/residual are indexed by m instead of n.
+  int transpose_out = 0;
+};
+
+struct GemmProblem {
+  CUtensorMap a_map;   // dims {K, M_rows, batch}, box {64, 128, 1}, SWIZZLE_128B
+  CUtensorMap w_map;   // dims {K, N},             box {64, BN},     SWIZZLE_128B
+  int M_rows = 0, batch = 1, N = 0, K = 0;
+  int bn = 256;        // 32 | 64 | 128 | 192 | 256  (must match w_map's box)
+  GemmEpilogue epi;
+};
+cudaError_t launch_gemm(const GemmProblem& g, int num_sms, cudaStream_t st);
+int gemm_pick_bn(int N);
+bool gemm_setup_attributes(const char** err);
+
+// ---- fused softmax attention (galois_flash_attn src/main.rs:1787-1797, call 1922) -------------
+struct AttnProblem {
+  CUtensorMap qk_map;  // dims {64, 2H, T, B} over the [B*T][2d] Q|K buffer, box {64,1,128,1}
+  CUtensorMap vt_map;  // dims {Tp, B*H*64} over V^T, box {64, 64}
+  int B = 0, T = 0, H = 0;
+  __half* out = nullptr;  // [B*T][H*64] merged heads (1924-1929)
+  float scale = 0.125f;
+};
+cudaError_t launch_attention(const AttnProblem& a, cudaStream_t st);
+bool attention_setup_attributes(const char** err);
+
+// ---- log-mel (src/main.rs:1554-1671) -----------------------------------------------------------
+struct MelTables {            // device pointers, built once per context
+  const float* hann;          // [400]
+  const float2* tw200;        // W_200^j, j < 200
+  const float2* tw400;        // W_400^k, k <= 200
+  const float* filt;          // [n_mel][201]
+  const int2* filt_range;     // per mel: [lo, hi) of nonzero taps
+  int n_mel;
+};
+// frames -> log10 mel power, [clip][n_mel][n_len]; also per-clip running max (ordered-int encoding)
+cudaError_t launch_mel_frames(const MelTables& t, const void* pcm, int pcm_is_i16, size_t n_samples,
+                              int n_clips, int n_len, float* mel_out, int* clip_max_enc, cudaStream_t st);
+// clamp_and_normalize (1654-1671): x = max(x, max - 8); x = (x + 4) / 4
+cudaError_t launch_mel_normalize(float* mel, int n_clips, size_t per_clip, const int* clip_max_enc, cudaStream_t st);
+cudaError_t launch_fill_i32(int* p, int n, int v, cudaStream_t st);
+
+// ---- small fused kernels -------------------------------------------------------------------------
+// E0 (1816-1829) + F16 rounding of the conv operand: [clip][n_mel][n_len] f32 window ->
+// [seg][Tm + 2][n_mel] f16 token-major with one zero row before and after.
+cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int* clip_ids,
+                              const long long* offsets, int n_seg, int Tm, __half* out, cudaStream_t st);
+// galois_norm + repeat/mul/add (1781-1785, 1882-1886): rows of d, f32 in; f16 and/or f32 out
+cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d,
+                             __half* out_f16, float* out_f32, cudaStream_t st);
+// sum|x| probes (1836-1849): out[seg] = sum over that segment's elements
+cudaError_t launch_abs_sum_f32(const float* x, long long per_seg, long long seg_stride, int n_seg, double* out,
+                               cudaStream_t st);
+cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long row_stride, long long seg_stride,
+                               int n_seg, double* out, cudaStream_t st);
+
+// ---- decoder step kernels (absent in the reference) ------------------------
+// D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
+cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
+                         int n_past, int d, float* x, cudaStream_t st);
+// self-attention over the F16 KV cache: q [n_seq*n_tok][ldq] (pre-scaled), cache [seq][n_text_ctx][d]
+cudaError_t launch_decode_self_attn(const __half* q, int ldq, const __half* kc, const __half* vc,
+                                    int n_seq, int n_tok, int n_past, int n_text_ctx, int H, __half* out,
+                                    cudaStream_t st);
+// cross-attention over the encoder memory: k/v rows at kv[(seg*T + t)*ld_kv + col0 + h*64 ..]
+cudaError_t launch_decode_cross_attn(const __half* q, int ldq, const __half* k, const __half* v, long long ld_kv,
+                                     int n_seq, int n_tok, int T, int H, __half* out, float* part_o,
+                                     float* part_ml, int n_split, cudaStream_t st);
+// K13: per-sequence arg-max (+ top-2 margin) over logits [n_seq][n_vocab]
+cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* tok, float* margin, cudaStream_t st);
+
+}  // namespace wb
