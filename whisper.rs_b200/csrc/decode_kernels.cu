@@ -1,3 +1,377 @@
-// decode_kernels.cu -- decoder-step kernels (filled in with the decoder milestone)
+// decode_kernels.cu -- decoder-step kernels (sm_100a, CUDA cores; every one is HBM-bound).
+//
+// The reference declares the decoder's state (WhisperLayerDecoder src/main.rs:694-731, memory_k/v
+// 1343-1347, memory_cross_k/v 1350-1354, logits 351-352) but implements no decode step; these
+// kernels implement SURVEY.md section 8a rows D1-D6 (upstream whisper.cpp v1.0.3 semantics) on
+// the state layout the reference's encoder leaves behind: F16 K/V, cross-K pre-scaled by
+// (d/H)^-1/4 (1994-1996), rows of d with each head's 64 values contiguous (128 bytes).
+//
+// Attention over a cache row-block is laid out so that 8 lanes read one 128-byte head row as
+// 8 x 16-byte chunks: every load instruction of a warp covers 4 full rows, fully coalesced.
 #include "ptx.cuh"
 #include "wb_kernels.hpp"
+
+namespace wb {
+
+namespace {
+
+constexpr int DH = 64;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ float block_max(float v, float* sh, int n_warps) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < n_warps; ++i) r = fmaxf(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.0f;
+  for (int i = 0; i < n_warps; ++i) r += sh[i];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// D1: x[s][i][:] = d_te[tok[s][i]][:] + d_pe[n_past + i][:]
+__global__ void embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
+                             int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x) {
+  const int row = blockIdx.x;   // s * n_tok + i
+  const int i = row % n_tok;
+  const int tok = tokens[row];
+  const int pos = *n_past_p + i;
+  const __half* e = te + (size_t)tok * d;
+  const float* p = pe + (size_t)pos * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) x[(size_t)row * d + c] = __half2float(e[c]) + p[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// D2: causal self-attention over the F16 KV cache, one CTA per (head, sequence).
+//   qkv   [n_seq*n_tok][3d] F16: Q and K already scaled by Dh^-1/4, V plain (GEMM epilogue)
+//   cache [seq][n_text_ctx][d] F16 for this layer; the CTA first appends its head's new K/V rows
+//         at positions n_past .. n_past+n_tok-1 (cache append of D2), then attends.
+// Probabilities are normalised and rounded to F16 before P.V, as ggml's mul_mat does to its
+// second operand when the first (V) is F16.
+constexpr int SELF_THREADS = 128;
+constexpr int SELF_MAX_CTX = 448 + 64;
+
+__global__ void __launch_bounds__(SELF_THREADS)
+decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restrict__ kc, __half* __restrict__ vc,
+                        int n_tok, const int* __restrict__ n_past_p, int n_text_ctx, __half* __restrict__ out) {
+  __shared__ float sc[SELF_MAX_CTX];
+  __shared__ float red[SELF_THREADS / 32];
+  __shared__ float opart[SELF_THREADS / 32][4][DH];
+  const int h = blockIdx.x, s = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_past = *n_past_p;
+  __half* kbase = kc + (size_t)s * n_text_ctx * d + h * DH;
+  __half* vbase = vc + (size_t)s * n_text_ctx * d + h * DH;
+  // append this head's new K / V rows (16-byte chunks)
+  for (int idx = tid; idx < n_tok * 8; idx += SELF_THREADS) {
+    const int i = idx >> 3, ch = idx & 7;
+    const __half* src = qkv + (size_t)(s * n_tok + i) * 3 * d + h * DH + ch * 8;
+    *reinterpret_cast<uint4*>(kbase + (size_t)(n_past + i) * d + ch * 8) = *reinterpret_cast<const uint4*>(src + d);
+    *reinterpret_cast<uint4*>(vbase + (size_t)(n_past + i) * d + ch * 8) = *reinterpret_cast<const uint4*>(src + 2 * d);
+  }
+  __syncthreads();
+  const int sub = lane >> 3, ch = lane & 7;   // 4 keys per warp instruction, 8 lanes per key row
+  for (int i = 0; i < n_tok; ++i) {
+    const int Tk = n_past + i + 1;            // causal: keys 0 .. n_past + i
+    float q[8];
+    unpack8(*reinterpret_cast<const uint4*>(qkv + (size_t)(s * n_tok + i) * 3 * d + h * DH + ch * 8), q);
+    for (int t0 = warp * 4; t0 < Tk; t0 += (SELF_THREADS / 32) * 4) {
+      const int t = t0 + sub;
+      float acc = 0.0f;
+      if (t < Tk) {
+        float kf[8];
+        unpack8(*reinterpret_cast<const uint4*>(kbase + (size_t)t * d + ch * 8), kf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(q[j], kf[j], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (ch == 0 && t < Tk) sc[t] = acc;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = tid; t < Tk; t += SELF_THREADS) mx = fmaxf(mx, sc[t]);
+    mx = block_max(mx, red, SELF_THREADS / 32);
+    float sum = 0.0f;
+    for (int t = tid; t < Tk; t += SELF_THREADS) {
+      const float e = __expf(sc[t] - mx);
+      sc[t] = e;
+      sum += e;
+    }
+    sum = block_sum(sum, red, SELF_THREADS / 32);
+    const float inv = 1.0f / sum;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int t0 = warp * 4; t0 < Tk; t0 += (SELF_THREADS / 32) * 4) {
+      const int t = t0 + sub;
+      if (t < Tk) {
+        const float p = __half2float(__float2half_rn(sc[t] * inv));
+        float vf[8];
+        unpack8(*reinterpret_cast<const uint4*>(vbase + (size_t)t * d + ch * 8), vf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) opart[warp][sub][ch * 8 + j] = o[j];
+    __syncthreads();
+    if (tid < DH) {
+      float r = 0.0f;
+#pragma unroll
+      for (int w = 0; w < SELF_THREADS / 32; ++w)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r += opart[w][u][tid];
+      out[(size_t)(s * n_tok + i) * d + h * DH + tid] = __float2half_rn(r);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// D3: cross-attention over the encoder memory (memory_cross_k/v), the decoder's dominant HBM
+// stream: 2 * T * 128 bytes per (sequence, head, layer) per generated token.
+//   q   [n_seq*n_tok][d] F16 (already scaled by Dh^-1/4)
+//   K/V rows: kv[(seq*T + t)*ld + h*64 ..], K at `k`, V at `v` (same row pitch)
+// grid (H, n_seq, n_split): each CTA handles keys [split*span, ...) for every query token; with
+// n_split > 1 it emits (max, sum, unnormalised o) partials that cross_combine_kernel merges.
+constexpr int CROSS_THREADS = 256;
+constexpr int CROSS_MAX_SPAN = 1536;
+
+__global__ void __launch_bounds__(CROSS_THREADS)
+decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
+                         long long ld, int n_tok, int T, int span, __half* __restrict__ out,
+                         float* __restrict__ part_o, float* __restrict__ part_ml, int n_split) {
+  __shared__ float sc[CROSS_MAX_SPAN];
+  __shared__ float red[CROSS_THREADS / 32];
+  __shared__ float opart[CROSS_THREADS / 32][4][DH];
+  const int h = blockIdx.x, s = blockIdx.y, sp = blockIdx.z, H = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane >> 3, ch = lane & 7;
+  const int t_lo = sp * span, t_hi = min(T, t_lo + span), n = t_hi - t_lo;
+  const __half* kb = k + ((size_t)s * T + t_lo) * ld + h * DH + ch * 8;
+  const __half* vb = v + ((size_t)s * T + t_lo) * ld + h * DH + ch * 8;
+  for (int i = 0; i < n_tok; ++i) {
+    const int row = s * n_tok + i;
+    float qf[8];
+    unpack8(*reinterpret_cast<const uint4*>(q + (size_t)row * d + h * DH + ch * 8), qf);
+    for (int t0 = warp * 4; t0 < n; t0 += (CROSS_THREADS / 32) * 4) {
+      const int t = t0 + sub;
+      float acc = 0.0f;
+      if (t < n) {
+        float kf[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(kb + (size_t)t * ld)), kf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(qf[j], kf[j], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (ch == 0 && t < n) sc[t] = acc;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = tid; t < n; t += CROSS_THREADS) mx = fmaxf(mx, sc[t]);
+    mx = block_max(mx, red, CROSS_THREADS / 32);
+    float sum = 0.0f;
+    for (int t = tid; t < n; t += CROSS_THREADS) {
+      const float e = __expf(sc[t] - mx);
+      sc[t] = e;
+      sum += e;
+    }
+    sum = block_sum(sum, red, CROSS_THREADS / 32);
+    const float inv = 1.0f / sum;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int t0 = warp * 4; t0 < n; t0 += (CROSS_THREADS / 32) * 4) {
+      const int t = t0 + sub;
+      if (t < n) {
+        const float p = __half2float(__float2half_rn(sc[t] * inv));   // P -> F16 before P.V
+        float vf[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(vb + (size_t)t * ld)), vf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) opart[warp][sub][ch * 8 + j] = o[j];
+    __syncthreads();
+    if (tid < DH) {
+      float r = 0.0f;
+#pragma unroll
+      for (int w = 0; w < CROSS_THREADS / 32; ++w)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r += opart[w][u][tid];
+      if (n_split == 1) {
+        out[(size_t)row * d + h * DH + tid] = __float2half_rn(r);
+      } else {
+        const size_t pi = ((size_t)row * H + h) * n_split + sp;
+        part_o[pi * DH + tid] = r;            // normalised within the split
+        if (tid == 0) {
+          part_ml[pi * 2] = mx;
+          part_ml[pi * 2 + 1] = sum;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// merge split partials: out = sum_s w_s o_s, w_s = l_s e^(m_s - m) / sum_s' l_s' e^(m_s' - m)
+__global__ void cross_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int n_split,
+                                     int d, __half* __restrict__ out) {
+  const int h = blockIdx.x, row = blockIdx.y, H = gridDim.x, c = threadIdx.x;
+  const size_t p0 = ((size_t)row * H + h) * n_split;
+  float m = -INFINITY;
+  for (int s = 0; s < n_split; ++s) m = fmaxf(m, part_ml[(p0 + s) * 2]);
+  float den = 0.0f, acc = 0.0f;
+  for (int s = 0; s < n_split; ++s) {
+    const float w = part_ml[(p0 + s) * 2 + 1] * __expf(part_ml[(p0 + s) * 2] - m);
+    den += w;
+    acc = fmaf(w, part_o[(p0 + s) * DH + c], acc);
+  }
+  out[(size_t)row * d + h * DH + c] = __float2half_rn(acc / den);
+}
+
+// ---------------------------------------------------------------------------------------------
+// D6 / K13: greedy selection.  Per sequence: arg-max over the logits (first index wins ties),
+// top-1 minus top-2 margin, then the loop bookkeeping of the device-side greedy decode:
+// record the token unless the sequence already emitted `eot`, feed it to the next step.
+struct Top2 {
+  float v1, v2;
+  int i1;
+};
+__device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
+  Top2 r;
+  if (b.v1 > a.v1 || (b.v1 == a.v1 && b.i1 < a.i1)) {
+    r.v1 = b.v1;
+    r.i1 = b.i1;
+    r.v2 = fmaxf(a.v1, b.v2);
+  } else {
+    r.v1 = a.v1;
+    r.i1 = a.i1;
+    r.v2 = fmaxf(a.v2, b.v1);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ next_tok, float* __restrict__ margin_out,
+              int* __restrict__ out_tokens, float* __restrict__ out_margin, int* __restrict__ out_len,
+              int* __restrict__ done, int max_new, const int* __restrict__ step_p, int eot) {
+  __shared__ Top2 sh[32];
+  const int s = blockIdx.x;
+  const float* lg = logits + (size_t)s * n_vocab;
+  Top2 t{-INFINITY, -INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+    const float v = lg[i];
+    if (v > t.v1) {
+      t.v2 = t.v1;
+      t.v1 = v;
+      t.i1 = i;
+    } else if (v > t.v2) {
+      t.v2 = v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Top2 u;
+    u.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+    u.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+    u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    t = top2_merge(t, u);
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Top2 r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = top2_merge(r, sh[w]);
+    next_tok[s] = r.i1;
+    if (margin_out) margin_out[s] = r.v1 - r.v2;
+    if (out_tokens) {
+      const int step = *step_p;
+      if (!done[s] && step < max_new) {
+        out_tokens[(size_t)s * max_new + step] = r.i1;
+        if (out_margin) out_margin[(size_t)s * max_new + step] = r.v1 - r.v2;
+        out_len[s] = step + 1;
+        if (r.i1 == eot) done[s] = 1;
+      }
+    }
+  }
+}
+
+__global__ void advance_kernel(int* n_past, int add, int* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    *n_past += add;
+    if (step) *step += 1;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
+                         const int* n_past_dev, int d, float* x, cudaStream_t st) {
+  embed_kernel<<<n_seq * n_tok, 128, 0, st>>>(te, pe, tokens, n_tok, n_past_dev, d, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
+                                    const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st) {
+  if (n_text_ctx > SELF_MAX_CTX) return cudaErrorInvalidValue;
+  decode_self_attn_kernel<<<dim3(H, n_seq), SELF_THREADS, 0, st>>>(qkv, d, kc, vc, n_tok, n_past_dev, n_text_ctx, out);
+  return cudaGetLastError();
+}
+
+int decode_cross_splits(int n_seq, int H, int T, int num_sms) {
+  int n_split = 1;
+  while (n_seq * H * n_split < 2 * num_sms && n_split < 8 && (T + n_split * 2 - 1) / (n_split * 2) >= 128) n_split *= 2;
+  return n_split;
+}
+
+cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, const __half* v, long long ld_kv,
+                                     int n_seq, int n_tok, int T, int H, __half* out, float* part_o, float* part_ml,
+                                     int n_split, cudaStream_t st) {
+  const int span = (T + n_split - 1) / n_split;
+  if (span > CROSS_MAX_SPAN) return cudaErrorInvalidValue;
+  decode_cross_attn_kernel<<<dim3(H, n_seq, n_split), CROSS_THREADS, 0, st>>>(q, d, k, v, ld_kv, n_tok, T, span, out,
+                                                                             part_o, part_ml, n_split);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || n_split == 1) return e;
+  cross_combine_kernel<<<dim3(H, n_seq * n_tok), DH, 0, st>>>(part_o, part_ml, n_split, d, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
+                          float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
+                          cudaStream_t st) {
+  argmax_kernel<<<n_seq, 1024, 0, st>>>(logits, n_vocab, next_tok, margin, out_tokens, out_margin, out_len, done,
+                                        max_new, step_dev, eot);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st) {
+  advance_kernel<<<1, 32, 0, st>>>(n_past_dev, add, step_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace wb
