@@ -97,6 +97,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
 int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out);        /* `cur` after ln_post (1980-1984): [n_ctx][d] f32 */
 int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v); /* F16 bits [n_ctx][d], 2018-2030 */
 int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum);
+/* sum|x| of every encoded segment's ln_post output in one call (the author's probe, 1836-1849, applied
+ * to `cur` after 1984): out[n_segments] doubles.  The small host-visible result of an encode step. */
+int wb_encoder_digest(wb_ctx* ctx, double* out, int cap);
 
 /* The decode step the reference declares state for but never implements (694-731, 1336-1354,
  * logits/probs 351-352): tokens is HOST [n_seqs][n_tokens]; sequence i attends to the cross K/V

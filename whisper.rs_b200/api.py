@@ -129,6 +129,11 @@ class WhisperContext:
         _check(cabi.lib().wb_checksum(self._h, stage, layer, seg, C.byref(v)), self._h)
         return v.value
 
+    def encoder_digest(self, n_seg: int) -> np.ndarray:
+        out = np.zeros(n_seg, dtype=np.float64)
+        _check(cabi.lib().wb_encoder_digest(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), n_seg), self._h)
+        return out
+
     def logits(self, seq: int = 0) -> np.ndarray:
         out = np.empty(self.n_vocab, dtype=np.float32)
         _check(cabi.lib().wb_logits_read(self._h, seq, _f32p(out)), self._h)

@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.wb_encoder_out_read.argtypes = [vp, C.c_int, f32p]
     L.wb_cross_kv_read.argtypes = [vp, C.c_int, C.c_int, u16p, u16p]
     L.wb_checksum.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.wb_encoder_digest.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     L.wb_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int]
     L.wb_logits_read.argtypes = [vp, C.c_int, f32p]
     L.wb_decode_greedy.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, f32p, i32p]

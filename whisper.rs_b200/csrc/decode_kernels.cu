@@ -157,7 +157,7 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
 constexpr int CROSS_THREADS = 256;
 constexpr int CROSS_MAX_SPAN = 1536;
 
-__global__ void __launch_bounds__(CROSS_THREADS)
+__global__ void __launch_bounds__(CROSS_THREADS, 3)
 decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
                          long long ld, int n_tok, int T, int span, __half* __restrict__ out,
                          float* __restrict__ part_o, float* __restrict__ part_ml, int n_split) {

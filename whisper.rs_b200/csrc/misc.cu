@@ -43,13 +43,14 @@ __global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int 
 constexpr int LN_MAX_V4 = 10;   // d <= 1280
 
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows,
-                 int d, __half* __restrict__ out_f16, float* __restrict__ out_f32) {
+layernorm_kernel(const float* __restrict__ x, long long in_row_stride, const float* __restrict__ w,
+                 const float* __restrict__ b, int rows, int d, __half* __restrict__ out_f16,
+                 float* __restrict__ out_f32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nv4 = d >> 2;   // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * in_row_stride);
   float4 v[LN_MAX_V4];
   float sum = 0.0f;
 #pragma unroll
@@ -143,11 +144,12 @@ cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int*
 }
 
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d, __half* out_f16,
-                             float* out_f32, cudaStream_t st) {
+                             float* out_f32, cudaStream_t st, long long in_row_stride) {
   if (d % 4 != 0 || d > 128 * LN_MAX_V4) return cudaErrorInvalidValue;
+  if (in_row_stride <= 0) in_row_stride = d;
   const int warps_per_block = 8;
-  layernorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(x, w, b, rows, d,
-                                                                                                  out_f16, out_f32);
+  layernorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(
+      x, in_row_stride, w, b, rows, d, out_f16, out_f32);
   return cudaGetLastError();
 }
 

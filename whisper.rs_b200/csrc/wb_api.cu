@@ -541,6 +541,7 @@ void wb_ctx_free(wb_ctx* ctx) {
   for (cudaEvent_t e : wb::g_free_events[ctx]) cudaEventDestroy(e);
   wb::g_free_events.erase(ctx);
   wb::g_pending.erase(ctx);
+  if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
   for (void* p : ctx->allocs) cudaFree(p);
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)
@@ -867,6 +868,20 @@ int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum) {
     return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: checkpoint not recorded (wb_config.checkpoints = 1?)");
   WB_CK(cudaMemcpyAsync(abs_sum, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments + seg, 8, cudaMemcpyDeviceToHost,
                         ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+int wb_encoder_digest(wb_ctx* ctx, double* out, int cap) {
+  if (!ctx || !out || ctx->enc_n_seg < 1 || cap < ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const long long n = (long long)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
+  {
+    LaunchTimer t(ctx, "digest");
+    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->stream));
+  }
+  WB_CK(cudaMemcpyAsync(out, slot, sizeof(double) * ctx->enc_n_seg, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
   return WB_OK;
 }

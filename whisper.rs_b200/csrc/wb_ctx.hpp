@@ -32,6 +32,10 @@ struct DecLayer {
   Linear qkv, out, cq, cout, fc1, fc2;
 };
 
+struct ActMaps {          // one activation buffer as the skinny GEMM operand, per tile width
+  CUtensorMap m[4];       // box {64, 32|64|128|256}
+};
+
 struct KernelClock {   // device time per kernel family (CUDA events on the handle's stream)
   double total_us = 0;
   int64_t launches = 0;
@@ -91,16 +95,19 @@ struct wb_ctx {
   std::vector<char> chk_valid;
 
   // ---- decoder state
-  __half *self_k = nullptr, *self_v = nullptr;   // [layer][seq][n_text_ctx][d]  (memory_k/v)
-  float* dx = nullptr;                           // residual [seq*n_tok][d]
-  __half *d_ln = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_hid = nullptr, *d_q = nullptr;
-  float* d_logits = nullptr;                     // [seq][n_vocab]
-  int* d_tokens = nullptr;
-  int *d_next = nullptr, *d_out_tokens = nullptr, *d_done = nullptr, *d_out_len = nullptr;
-  float* d_margin = nullptr;
+  int dec_rows_cap = 0;                          // rows (sequences x tokens) one wb_decode call may carry
+  __half *self_k = nullptr, *self_v = nullptr;   // [layer][seq][n_text_ctx][d] F16  (memory_k/v, 1343-1347)
+  float* dx = nullptr;                           // residual stream [rows][d] f32
+  __half *d_ln = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_hid = nullptr, *d_q = nullptr, *d_lnf = nullptr;
+  wb::ActMaps m_ln, m_att, m_hid, m_lnf;         // swap-AB activation operands
+  float* d_logits = nullptr;                     // [seq][n_vocab] of the last position  (logits, 351)
+  int *d_tokens = nullptr, *d_next = nullptr, *d_out_tokens = nullptr, *d_done = nullptr, *d_out_len = nullptr;
+  int *d_npast = nullptr, *d_step = nullptr;
+  float *d_margin = nullptr, *d_out_margin = nullptr;
   float *d_part_o = nullptr, *d_part_ml = nullptr;
-  int dec_max_tok = 0;
   int dec_n_seq = 0;
+  cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
+  int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;
 
   // ---- timing
   cudaEvent_t ev[3][2] = {};          // [mel|encode|decode][start|stop] of the most recent call

@@ -1,22 +1,380 @@
-// wb_decode.cu -- decoder step (placeholder until the kernels land)
+// wb_decode.cu -- the decode step + device-side greedy loop behind wb_decode / wb_decode_greedy.
+//
+// The reference stops after whisper_encode (src/main.rs:2065-2075); it declares the decoder's
+// weights (WhisperLayerDecoder 694-731, tensor table 1139-1333), the self-attention KV cache
+// memory_k/v (F16 [n_text_layer * n_text_ctx * n_text_state], 1343-1347) and logits/probs
+// (351-352) but no function that uses them.  This file implements SURVEY.md section 8a rows
+// D1-D6 (upstream whisper.cpp v1.0.3 semantics) on that state.
+//
+// Every linear layer runs on the tcgen05 GEMM in swap-AB form: the weight [N_out][K] is the
+// 128-row "A" operand streamed once from HBM by TMA, the few activation rows (sequences x
+// tokens) are the narrow N tile, and the epilogue stores C^T so activations stay token-major.
+// n_past and the greedy step counter live in device memory, so one captured CUDA graph replays
+// for every position of the greedy loop (the step is launch-bound otherwise).
+#include <math.h>
+#include <string.h>
+
 #include "wb_internal.hpp"
 
 namespace wb {
-int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
-  (void)ctx;
-  (void)mv;
+
+static int bn_for_rows(int R) { return R <= 32 ? 32 : R <= 64 ? 64 : R <= 128 ? 128 : 256; }
+static int bn_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3; }
+
+static int make_act_maps(wb_ctx* ctx, ActMaps& am, const __half* base, int K, int rows_cap) {
+  const int bns[4] = {32, 64, 128, 256};
+  const char* err = "";
+  for (int i = 0; i < 4; ++i) {
+    if (!tmap_2d_rows(&am.m[i], base, (uint64_t)K, (uint64_t)rows_cap, (uint64_t)K, (uint32_t)bns[i], &err))
+      return fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + err + "'");
+  }
   return WB_OK;
 }
+
+// C^T = W * X^T : out[r][n_out] for r < R
+static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, int R, GemmEpilogue epi,
+                            const char* family) {
+  GemmProblem g;
+  g.a_map = l.map_a;
+  const int bn = bn_for_rows(R);
+  g.w_map = act.m[bn_index(bn)];
+  g.M_rows = l.N;
+  g.batch = 1;
+  g.N = R;
+  g.K = l.K;
+  g.bn = bn;
+  epi.transpose_out = 1;
+  if (!epi.bias) epi.bias = l.bias;
+  if (!epi.colscale) epi.colscale = l.colscale;
+  g.epi = epi;
+  LaunchTimer t(ctx, family);
+  WB_CK(launch_gemm(g, ctx->num_sms, ctx->stream));
+  return WB_OK;
+}
+
+int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
+  const ModelHParams& hp = ctx->hp;
+  const int d = hp.n_text_state, Lt = hp.n_text_layer, S = ctx->cfg.max_segments;
+  const float s = powf((float)d / (float)hp.n_text_head, -0.25f);   // Dh^-1/4 on Q and K (D2, D3)
+  int rc;
+  // token embedding doubles as the logits projection (D5): d_te [n_vocab][d]
+  if ((rc = upload_linear(ctx, mv, "decoder.token_embedding.weight", "", ctx->logits_lin, true))) return rc;
+  ctx->d_te = ctx->logits_lin.w;
+  if ((rc = upload_f32(ctx, mv, "decoder.positional_embedding", &ctx->d_pe))) return rc;
+  if ((rc = upload_f32(ctx, mv, "decoder.ln.weight", &ctx->d_ln_w))) return rc;
+  if ((rc = upload_f32(ctx, mv, "decoder.ln.bias", &ctx->d_ln_b))) return rc;
+  ctx->dec.resize(Lt);
+  for (int i = 0; i < Lt; ++i) {
+    const std::string p = "decoder.blocks." + std::to_string(i) + ".";
+    DecLayer& l = ctx->dec[i];
+    if ((rc = upload_f32(ctx, mv, p + "attn_ln.weight", &l.attn_ln_w))) return rc;
+    if ((rc = upload_f32(ctx, mv, p + "attn_ln.bias", &l.attn_ln_b))) return rc;
+    if ((rc = upload_f32(ctx, mv, p + "cross_attn_ln.weight", &l.cross_ln_w))) return rc;
+    if ((rc = upload_f32(ctx, mv, p + "cross_attn_ln.bias", &l.cross_ln_b))) return rc;
+    if ((rc = upload_f32(ctx, mv, p + "mlp_ln.weight", &l.mlp_ln_w))) return rc;
+    if ((rc = upload_f32(ctx, mv, p + "mlp_ln.bias", &l.mlp_ln_b))) return rc;
+    // Q = (Wq x + bq) * s ; K = (Wk x) * s ; V = Wv x + bv   (D2)
+    if ((rc = upload_cat(ctx, mv,
+                         {{p + "attn.query.weight", p + "attn.query.bias", s},
+                          {p + "attn.key.weight", "", s},
+                          {p + "attn.value.weight", p + "attn.value.bias", 1.0f}},
+                         l.qkv, true)))
+      return rc;
+    if ((rc = upload_linear(ctx, mv, p + "attn.out.weight", p + "attn.out.bias", l.out, true))) return rc;
+    if ((rc = upload_cat(ctx, mv, {{p + "cross_attn.query.weight", p + "cross_attn.query.bias", s}}, l.cq, true)))
+      return rc;
+    if ((rc = upload_linear(ctx, mv, p + "cross_attn.out.weight", p + "cross_attn.out.bias", l.cout, true))) return rc;
+    if ((rc = upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, true))) return rc;
+    if ((rc = upload_linear(ctx, mv, p + "mlp.2.weight", p + "mlp.2.bias", l.fc2, true))) return rc;
+  }
+  // ---- state
+  const size_t n_ctx = hp.n_text_ctx;
+  size_t R = (size_t)S * n_ctx;
+  if (R < 256) R = 256;
+  ctx->dec_rows_cap = (int)R;
+  if ((rc = dev_alloc(ctx, &ctx->self_k, (size_t)Lt * S * n_ctx * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->self_v, (size_t)Lt * S * n_ctx * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->dx, R * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_ln, R * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_qkv, R * 3 * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_att, R * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_q, R * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_hid, R * 4 * d))) return rc;
+  const size_t Sf = S < 256 ? 256 : S;
+  if ((rc = dev_alloc(ctx, &ctx->d_lnf, Sf * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_logits, (size_t)S * hp.n_vocab))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_tokens, R))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_next, (size_t)S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_out_tokens, (size_t)S * n_ctx))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_out_margin, (size_t)S * n_ctx))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_margin, (size_t)S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_out_len, (size_t)S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_done, (size_t)S))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_npast, 4))) return rc;
+  ctx->d_step = ctx->d_npast + 1;
+  // split-K cross-attention partials (only used for few rows: n_tok <= 8)
+  const size_t prow = (size_t)S * 8 * hp.n_text_head * 8;
+  if ((rc = dev_alloc(ctx, &ctx->d_part_o, prow * 64))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_part_ml, prow * 2))) return rc;
+  if ((rc = make_act_maps(ctx, ctx->m_ln, ctx->d_ln, d, (int)R))) return rc;
+  if ((rc = make_act_maps(ctx, ctx->m_att, ctx->d_att, d, (int)R))) return rc;
+  if ((rc = make_act_maps(ctx, ctx->m_hid, ctx->d_hid, 4 * d, (int)R))) return rc;
+  if ((rc = make_act_maps(ctx, ctx->m_lnf, ctx->d_lnf, d, (int)Sf))) return rc;
+  return WB_OK;
+}
+
+// One decode pass over `n_tok` new tokens per sequence: embed -> L x (self-attn, cross-attn, MLP)
+// -> final LN of the last position -> logits.  Launch-only (no host sync, no copies): capturable.
+static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok) {
+  const ModelHParams& hp = ctx->hp;
+  const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, T = hp.n_audio_ctx;
+  const int n_ctx = hp.n_text_ctx;
+  const int R = n_seq * n_tok;
+  const long long ld_kv = (long long)Lt * 2 * d;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  {
+    LaunchTimer t(ctx, "dec_embed");
+    WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, ctx->dx, st));
+  }
+  const int n_split = n_tok <= 8 ? decode_cross_splits(n_seq, H, T, ctx->num_sms) : 1;
+  for (int il = 0; il < Lt; ++il) {
+    const DecLayer& l = ctx->dec[il];
+    {   // D2: self-attention
+      LaunchTimer t(ctx, "dec_layernorm");
+      WB_CK(launch_layernorm(ctx->dx, l.attn_ln_w, l.attn_ln_b, R, d, ctx->d_ln, nullptr, st));
+    }
+    {
+      GemmEpilogue e;
+      e.out = ctx->d_qkv;
+      e.out_f16 = 1;
+      e.out_ld = 3 * d;
+      if ((rc = run_gemm_swapped(ctx, l.qkv, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+    }
+    {
+      LaunchTimer t(ctx, "dec_self_attn");
+      __half* kc = ctx->self_k + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
+      __half* vc = ctx->self_v + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
+      WB_CK(launch_decode_self_attn(ctx->d_qkv, d, kc, vc, n_seq, n_tok, ctx->d_npast, n_ctx, H, ctx->d_att, st));
+    }
+    {
+      GemmEpilogue e;
+      e.residual = ctx->dx;
+      e.res_ld = d;
+      e.out = ctx->dx;
+      e.out_f16 = 0;
+      e.out_ld = d;
+      if ((rc = run_gemm_swapped(ctx, l.out, ctx->m_att, R, e, "dec_gemm"))) return rc;
+    }
+    {   // D3: cross-attention over memory_cross_k/v written by wb_encode
+      LaunchTimer t(ctx, "dec_layernorm");
+      WB_CK(launch_layernorm(ctx->dx, l.cross_ln_w, l.cross_ln_b, R, d, ctx->d_ln, nullptr, st));
+    }
+    {
+      GemmEpilogue e;
+      e.out = ctx->d_q;
+      e.out_f16 = 1;
+      e.out_ld = d;
+      if ((rc = run_gemm_swapped(ctx, l.cq, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+    }
+    {
+      LaunchTimer t(ctx, "dec_cross_attn");
+      const __half* kx = ctx->cross + (size_t)il * 2 * d;
+      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + d, ld_kv, n_seq, n_tok, T, H, ctx->d_att, ctx->d_part_o,
+                                     ctx->d_part_ml, n_split, st));
+    }
+    {
+      GemmEpilogue e;
+      e.residual = ctx->dx;
+      e.res_ld = d;
+      e.out = ctx->dx;
+      e.out_f16 = 0;
+      e.out_ld = d;
+      if ((rc = run_gemm_swapped(ctx, l.cout, ctx->m_att, R, e, "dec_gemm"))) return rc;
+    }
+    {   // D4: MLP
+      LaunchTimer t(ctx, "dec_layernorm");
+      WB_CK(launch_layernorm(ctx->dx, l.mlp_ln_w, l.mlp_ln_b, R, d, ctx->d_ln, nullptr, st));
+    }
+    {
+      GemmEpilogue e;
+      e.gelu = 1;
+      e.out = ctx->d_hid;
+      e.out_f16 = 1;
+      e.out_ld = 4 * d;
+      if ((rc = run_gemm_swapped(ctx, l.fc1, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+    }
+    {
+      GemmEpilogue e;
+      e.residual = ctx->dx;
+      e.res_ld = d;
+      e.out = ctx->dx;
+      e.out_f16 = 0;
+      e.out_ld = d;
+      if ((rc = run_gemm_swapped(ctx, l.fc2, ctx->m_hid, R, e, "dec_gemm"))) return rc;
+    }
+  }
+  {   // D5: logits of the last position of every sequence
+    LaunchTimer t(ctx, "dec_layernorm");
+    WB_CK(launch_layernorm(ctx->dx + (size_t)(n_tok - 1) * d, ctx->d_ln_w, ctx->d_ln_b, n_seq, d, ctx->d_lnf, nullptr,
+                           st, (long long)n_tok * d));
+  }
+  {
+    GemmEpilogue e;
+    e.out = ctx->d_logits;
+    e.out_f16 = 0;
+    e.out_ld = hp.n_vocab;
+    if ((rc = run_gemm_swapped(ctx, ctx->logits_lin, ctx->m_lnf, n_seq, e, "dec_gemm_logits"))) return rc;
+  }
+  return WB_OK;
+}
+
+static int check_decode_args(wb_ctx* ctx, int n_tok, int n_past, int n_seq) {
+  if (!ctx->cfg.decode_capacity || !ctx->self_k)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: context created without decode_capacity");
+  if (n_seq < 1 || n_seq > ctx->cfg.max_segments || n_tok < 1 || n_past < 0 ||
+      n_past + n_tok > ctx->hp.n_text_ctx || (long long)n_seq * n_tok > ctx->dec_rows_cap)
+    return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  if (n_seq > ctx->enc_n_seg)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: decode needs the cross K/V of wb_encode for every sequence");
+  return WB_OK;
+}
+
 }  // namespace wb
 
+using namespace wb;
+
 extern "C" {
-int wb_decode(wb_ctx* ctx, const int32_t*, int, int, int) {
-  return wb::fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: wb_decode not built yet");
+
+int wb_decode(wb_ctx* ctx, const int32_t* tokens, int n_tokens, int n_past, int n_seqs) {
+  if (!ctx || !tokens) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  int rc = check_decode_args(ctx, n_tokens, n_past, n_seqs);
+  if (rc) return rc;
+  const int R = n_seqs * n_tokens;
+  for (int i = 0; i < R; ++i)
+    if (tokens[i] < 0 || tokens[i] >= ctx->hp.n_vocab) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: token id out of range");
+  cudaStream_t st = ctx->stream;
+  cudaEventRecord(ctx->ev[2][0], st);
+  WB_CK(cudaMemcpyAsync(ctx->d_tokens, tokens, sizeof(int) * R, cudaMemcpyHostToDevice, st));
+  WB_CK(launch_fill_i32(ctx->d_npast, 1, n_past, st));
+  rc = decode_pass(ctx, ctx->d_tokens, n_seqs, n_tokens);
+  if (rc) return rc;
+  cudaEventRecord(ctx->ev[2][1], st);
+  ctx->ev_used[2] = true;
+  ctx->dec_n_seq = n_seqs;
+  ctx->tm.n_decode_calls += 1;
+  WB_CK(cudaStreamSynchronize(st));   // `tokens` is caller memory: the H2D copy must have drained
+  return WB_OK;
 }
-int wb_logits_read(wb_ctx* ctx, int, float*) {
-  return wb::fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: wb_decode not built yet");
+
+int wb_logits_read(wb_ctx* ctx, int seq, float* out) {
+  if (!ctx || !out || seq < 0 || seq >= ctx->dec_n_seq) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->hp.n_vocab;
+  WB_CK(cudaMemcpyAsync(out, ctx->d_logits + (size_t)seq * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
 }
-int wb_decode_greedy(wb_ctx* ctx, const int32_t*, int, int, int, int, int32_t*, float*, int32_t*) {
-  return wb::fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: wb_decode not built yet");
+
+// D6: greedy = arg-max over all logits; prompt shared by all sequences; a sequence stops recording
+// after `eot` or max_new tokens or when the text context is full.
+int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_new, int eot, int n_seqs,
+                     int32_t* out_tokens, float* out_margin, int32_t* out_len) {
+  if (!ctx || !prompt || !out_tokens || !out_len || max_new < 1) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  int rc = check_decode_args(ctx, n_prompt, 0, n_seqs);
+  if (rc) return rc;
+  const ModelHParams& hp = ctx->hp;
+  const int n_ctx = hp.n_text_ctx;
+  if (max_new > n_ctx) max_new = n_ctx;
+  cudaStream_t st = ctx->stream;
+  std::vector<int> toks((size_t)n_seqs * n_prompt);
+  for (int s = 0; s < n_seqs; ++s)
+    for (int i = 0; i < n_prompt; ++i) {
+      if (prompt[i] < 0 || prompt[i] >= hp.n_vocab) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: token id out of range");
+      toks[(size_t)s * n_prompt + i] = prompt[i];
+    }
+  cudaEventRecord(ctx->ev[2][0], st);
+  WB_CK(cudaMemcpyAsync(ctx->d_tokens, toks.data(), sizeof(int) * toks.size(), cudaMemcpyHostToDevice, st));
+  WB_CK(cudaMemsetAsync(ctx->d_done, 0, sizeof(int) * n_seqs, st));
+  WB_CK(cudaMemsetAsync(ctx->d_out_len, 0, sizeof(int) * n_seqs, st));
+  WB_CK(cudaMemsetAsync(ctx->d_npast, 0, sizeof(int) * 2, st));   // n_past = 0, step = 0
+  // out buffers are indexed [seq][max_new]
+  WB_CK(cudaMemsetAsync(ctx->d_out_tokens, 0, sizeof(int) * (size_t)n_seqs * max_new, st));
+  WB_CK(cudaMemsetAsync(ctx->d_out_margin, 0, sizeof(float) * (size_t)n_seqs * max_new, st));
+  // ---- prompt pass
+  if ((rc = decode_pass(ctx, ctx->d_tokens, n_seqs, n_prompt))) return rc;
+  {
+    LaunchTimer t(ctx, "dec_argmax");
+    WB_CK(launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
+                        ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st));
+    WB_CK(launch_advance(ctx->d_npast, n_prompt, ctx->d_step, st));
+  }
+  WB_CK(cudaStreamSynchronize(st));   // `toks` is a stack temporary
+  // ---- single-token steps: captured once, replayed for every position
+  int n_past = n_prompt;
+  const int n_steps_max = max_new - 1;
+  const bool use_graph = !ctx->time_kernels;
+  if (use_graph && (ctx->step_graph == nullptr || ctx->step_graph_n_seq != n_seqs ||
+                    ctx->step_graph_max_new != max_new || ctx->step_graph_eot != eot)) {
+    if (ctx->step_graph) {
+      cudaGraphExecDestroy(ctx->step_graph);
+      ctx->step_graph = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    WB_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (rc == WB_OK) {
+      e1 = launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
+                         ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st);
+      e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
+    }
+    cudaError_t e3 = cudaStreamEndCapture(st, &graph);
+    if (rc != WB_OK) return rc;
+    if (e1 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "argmax (capture)", e1);
+    if (e2 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "advance (capture)", e2);
+    if (e3 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaStreamEndCapture", e3);
+    cudaError_t e4 = cudaGraphInstantiate(&ctx->step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e4 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaGraphInstantiate", e4);
+    ctx->step_graph_n_seq = n_seqs;
+    ctx->step_graph_max_new = max_new;
+    ctx->step_graph_eot = eot;
+  }
+  std::vector<int> done_h(n_seqs, 0);
+  for (int it = 0; it < n_steps_max; ++it) {
+    if (n_past + 1 > n_ctx) break;   // text context full
+    if (use_graph) {
+      WB_CK(cudaGraphLaunch(ctx->step_graph, st));
+      ctx->tm.n_kernel_launches += 9 * hp.n_text_layer + 5;
+    } else {
+      if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
+      LaunchTimer t(ctx, "dec_argmax");
+      WB_CK(launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
+                          ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st));
+      WB_CK(launch_advance(ctx->d_npast, 1, ctx->d_step, st));
+    }
+    n_past += 1;
+    if ((it & 31) == 31) {   // every 32 steps: stop early once every sequence has emitted eot
+      WB_CK(cudaMemcpyAsync(done_h.data(), ctx->d_done, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, st));
+      WB_CK(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int v : done_h) all = all && v != 0;
+      if (all) break;
+    }
+  }
+  cudaEventRecord(ctx->ev[2][1], st);
+  ctx->ev_used[2] = true;
+  ctx->dec_n_seq = n_seqs;
+  ctx->tm.n_decode_calls += 1;
+  WB_CK(cudaMemcpyAsync(out_tokens, ctx->d_out_tokens, sizeof(int) * (size_t)n_seqs * max_new, cudaMemcpyDeviceToHost, st));
+  if (out_margin)
+    WB_CK(cudaMemcpyAsync(out_margin, ctx->d_out_margin, sizeof(float) * (size_t)n_seqs * max_new, cudaMemcpyDeviceToHost, st));
+  WB_CK(cudaMemcpyAsync(out_len, ctx->d_out_len, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, st));
+  WB_CK(cudaStreamSynchronize(st));
+  return WB_OK;
 }
-}
+
+}  // extern "C"

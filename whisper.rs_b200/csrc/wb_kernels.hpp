@@ -87,7 +87,7 @@ cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int*
                               const long long* offsets, int n_seg, int Tm, __half* out, cudaStream_t st);
 // galois_norm + repeat/mul/add (1781-1785, 1882-1886): rows of d, f32 in; f16 and/or f32 out
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d,
-                             __half* out_f16, float* out_f32, cudaStream_t st);
+                             __half* out_f16, float* out_f32, cudaStream_t st, long long in_row_stride = 0);
 // sum|x| probes (1836-1849): out[seg] = sum over that segment's elements
 cudaError_t launch_abs_sum_f32(const float* x, long long per_seg, long long seg_stride, int n_seg, double* out,
                                cudaStream_t st);
@@ -95,18 +95,22 @@ cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long ro
                                int n_seg, double* out, cudaStream_t st);
 
 // ---- decoder step kernels (absent in the reference) ------------------------
+// n_past / step live in device memory so one captured CUDA graph serves every position.
 // D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
-                         int n_past, int d, float* x, cudaStream_t st);
-// self-attention over the F16 KV cache: q [n_seq*n_tok][ldq] (pre-scaled), cache [seq][n_text_ctx][d]
-cudaError_t launch_decode_self_attn(const __half* q, int ldq, const __half* kc, const __half* vc,
-                                    int n_seq, int n_tok, int n_past, int n_text_ctx, int H, __half* out,
-                                    cudaStream_t st);
-// cross-attention over the encoder memory: k/v rows at kv[(seg*T + t)*ld_kv + col0 + h*64 ..]
-cudaError_t launch_decode_cross_attn(const __half* q, int ldq, const __half* k, const __half* v, long long ld_kv,
-                                     int n_seq, int n_tok, int T, int H, __half* out, float* part_o,
-                                     float* part_ml, int n_split, cudaStream_t st);
-// K13: per-sequence arg-max (+ top-2 margin) over logits [n_seq][n_vocab]
-cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* tok, float* margin, cudaStream_t st);
+                         const int* n_past_dev, int d, float* x, cudaStream_t st);
+// D2: append this step's K/V to the F16 cache [seq][n_text_ctx][d], causal attention over it
+cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
+                                    const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st);
+// D3: cross-attention over the encoder memory; rows at kv[(seq*T + t)*ld_kv + h*64 ..]
+int decode_cross_splits(int n_seq, int H, int T, int num_sms);
+cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, const __half* v, long long ld_kv,
+                                     int n_seq, int n_tok, int T, int H, __half* out, float* part_o, float* part_ml,
+                                     int n_split, cudaStream_t st);
+// D6 / K13: per-sequence arg-max + top-2 margin + greedy-loop bookkeeping
+cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
+                          float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
+                          cudaStream_t st);
+cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st);
 
 }  // namespace wb
