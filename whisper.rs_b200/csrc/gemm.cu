@@ -31,8 +31,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;           // one 128-byte swizzle atom of f16
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 
 struct GemmArgs {
   int M_rows, batch, N, K;
@@ -97,7 +98,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -171,6 +172,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
     // ===================== epilogue =====================
     const GemmEpilogue& e = args.e;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int chunk0 = (warp - EPI_WARP0) >> 2;   // 0 or 1: which interleaved half of the column chunks
     const int row_in_tile = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++it) {
@@ -187,7 +189,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chunk0; c < BN / 32; c += EPI_WARPS / 4) {
         const int n0 = nt * BN + c * 32;
         if (n0 >= args.N) break;            // warp-uniform
         uint32_t raw[32];
@@ -199,14 +201,32 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
         const bool full_chunk = (n0 + 32 <= args.N);
         if (!e.transpose_out) {
           if (e.bias) {
+            if (full_chunk) {
+              const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full_chunk || n0 + j < args.N) v[j] += __ldg(e.bias + n0 + j);
+              for (int qd = 0; qd < 8; ++qd) {
+                const float4 bb = __ldg(b4 + qd);
+                v[4 * qd] += bb.x; v[4 * qd + 1] += bb.y; v[4 * qd + 2] += bb.z; v[4 * qd + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < args.N) v[j] += __ldg(e.bias + n0 + j);
+            }
           }
           if (e.colscale) {
+            if (full_chunk) {
+              const float4* c4 = reinterpret_cast<const float4*>(e.colscale + n0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full_chunk || n0 + j < args.N) v[j] *= __ldg(e.colscale + n0 + j);
+              for (int qd = 0; qd < 8; ++qd) {
+                const float4 cc = __ldg(c4 + qd);
+                v[4 * qd] *= cc.x; v[4 * qd + 1] *= cc.y; v[4 * qd + 2] *= cc.z; v[4 * qd + 3] *= cc.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < args.N) v[j] *= __ldg(e.colscale + n0 + j);
+            }
           }
         } else if (row_ok) {
           if (e.bias) {

@@ -197,10 +197,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 // ggml-sem GELU (galois_gelu src/main.rs:1777): tanh approximation,
 // input rounded to F16 first; the caller rounds the result to F16 when it stores it.
+// tanh through the MUFU unit (tanh.approx.f32, rel. error ~2^-11): the result is rounded to F16
+// (2^-11) by every caller, so the approximation stays inside the rounding the reference applies.
 __device__ __forceinline__ float gelu_f16in(float x) {
   x = __half2float(__float2half_rn(x));
-  const float u = 0.79788456080286535588f * x * (1.0f + 0.044715f * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  const float u = 0.79788456080286535588f * x * fmaf(0.044715f * x, x, 1.0f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 }  // namespace wb
