@@ -267,7 +267,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
           // V^T scatter: time contiguous (reference layout [T, Dh, H], src/main.rs:1914-1920)
           const int seg = m / e.vt_T;
           const int t = m - seg * e.vt_T;
-          __half* dst = e.vt_out + ((long long)seg * e.vt_rows + (n0 - e.vt_col0)) * e.vt_ld + t;
+          const int nn = n0 - e.vt_col0;   // multiple of 32: the chunk lies inside one head
+          __half* dst = e.vt_out + ((long long)(seg * e.vt_heads + (nn >> 6)) * e.vt_head_rows + (nn & 63)) * e.vt_ld + t;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (full_chunk || n0 + j < args.N) dst[(long long)j * e.vt_ld] = __float2half_rn(v[j]);

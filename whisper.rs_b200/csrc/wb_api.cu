@@ -3,6 +3,7 @@
 // whisper_encode (src/main.rs:2065-2075) behind include/whisper_b200.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -356,7 +357,8 @@ int alloc_activations(wb_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->x, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->ln_out, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->qk, S * T * 2 * d))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->vt, S * d * ctx->Tp))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->vt, S * (d / 64) * ATTN_VT_HEAD_ROWS * ctx->Tp))) return rc;
+  WB_CK(launch_vt_init(ctx->vt, (int)(S * (d / 64)), ctx->Tp, ctx->stream));
   if ((rc = dev_alloc(ctx, &ctx->attn_out, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->hidden, S * T * 4 * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->enc_out, S * T * d))) return rc;
@@ -704,9 +706,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     ok = make_tmap_f16(&ap.qk_map, ctx->qk, 4, dims, strd, box, &terr);
   }
   if (ok) {
-    const uint64_t dims[2] = {(uint64_t)ctx->Tp, (uint64_t)n_seg * d};
+    const uint64_t dims[2] = {(uint64_t)ctx->Tp, (uint64_t)n_seg * H * ATTN_VT_HEAD_ROWS};
     const uint64_t strd[1] = {(uint64_t)ctx->Tp * 2};
-    const uint32_t box[2] = {64, 64};
+    const uint32_t box[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
     ok = make_tmap_f16(&ap.vt_map, ctx->vt, 2, dims, strd, box, &terr);
   }
   if (!ok) return fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
@@ -771,7 +773,8 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out_ld = 2 * d;
       e.vt_out = ctx->vt;
       e.vt_col0 = 2 * d;
-      e.vt_rows = d;
+      e.vt_heads = H;
+      e.vt_head_rows = ATTN_VT_HEAD_ROWS;
       e.vt_ld = ctx->Tp;
       e.vt_T = T;
       if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e))) return rc;
@@ -1015,12 +1018,15 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
   const char* terr = "";
   auto cleanup = [&]() { cudaFree(dQK); cudaFree(dVt); cudaFree(dO); };
   // host repack: Q|K rows [M][2d]; V^T [seg][d][Tp]
-  std::vector<uint16_t> qk(M * 2 * d), vt((size_t)n_seg * d * Tp, 0);
+  const int VR = ATTN_VT_HEAD_ROWS;
+  std::vector<uint16_t> qk(M * 2 * d), vt((size_t)n_seg * H * VR * Tp, 0);
   for (size_t m = 0; m < M; ++m) {
     memcpy(&qk[m * 2 * d], &qkv_f16[m * 3 * d], (size_t)2 * d * 2);
     const size_t seg = m / T, t = m % T;
-    for (int c = 0; c < d; ++c) vt[(seg * d + c) * Tp + t] = qkv_f16[m * 3 * d + 2 * d + c];
+    for (int c = 0; c < d; ++c) vt[((seg * H + c / 64) * VR + c % 64) * Tp + t] = qkv_f16[m * 3 * d + 2 * d + c];
   }
+  for (size_t hb = 0; hb < (size_t)n_seg * H; ++hb)   // the ones row behind every head block
+    for (int t = 0; t < Tp; ++t) vt[(hb * VR + 64) * Tp + t] = 0x3C00;
   DBG_CK(cudaMalloc(&dQK, qk.size() * 2));
   DBG_CK(cudaMalloc(&dVt, vt.size() * 2));
   DBG_CK(cudaMalloc(&dO, M * d * 2));
@@ -1032,9 +1038,9 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
     const uint64_t dims[4] = {64, (uint64_t)2 * H, (uint64_t)T, (uint64_t)n_seg};
     const uint64_t strd[3] = {128, (uint64_t)2 * d * 2, (uint64_t)T * 2 * d * 2};
     const uint32_t box[4] = {64, 1, 128, 1};
-    const uint64_t dims2[2] = {(uint64_t)Tp, (uint64_t)n_seg * d};
+    const uint64_t dims2[2] = {(uint64_t)Tp, (uint64_t)n_seg * H * ATTN_VT_HEAD_ROWS};
     const uint64_t strd2[1] = {(uint64_t)Tp * 2};
-    const uint32_t box2[2] = {64, 64};
+    const uint32_t box2[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
     if (!make_tmap_f16(&ap.qk_map, dQK, 4, dims, strd, box, &terr) ||
         !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr)) {
       fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
@@ -1047,11 +1053,27 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
   ap.H = H;
   ap.out = dO;
   ap.scale = 0.125f;
+  long long* d_trace = nullptr;
+  const char* trace_path = getenv("WB_ATTN_TRACE");   // developer aid: per-phase clock64() trace of CTA (0,0,0)
+  if (trace_path) {
+    DBG_CK(cudaMalloc(&d_trace, 1024 * sizeof(long long)));
+    DBG_CK(cudaMemset(d_trace, 0, 1024 * sizeof(long long)));
+    ap.dbg = d_trace;
+  }
   {
     LaunchTimer t(ctx, "dbg_attention");
     DBG_CK(launch_attention(ap, ctx->stream));
   }
   DBG_CK(cudaStreamSynchronize(ctx->stream));
+  if (d_trace) {
+    std::vector<long long> h(1024);
+    cudaMemcpy(h.data(), d_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int i = 0; i < 1024; ++i) fprintf(f, "%lld\n", h[i]);
+      fclose(f);
+    }
+  }
   DBG_CK(cudaMemcpy(out_f16, dO, M * d * 2, cudaMemcpyDeviceToHost));
   cleanup();
   return rc;

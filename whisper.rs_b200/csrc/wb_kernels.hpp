@@ -29,12 +29,14 @@ struct GemmEpilogue {
   int out_f16 = 1;
   long long out_bstride = 0;
   int out_ld = 0;
-  // columns n >= vt_col0 are written transposed (time contiguous) as F16:
-  //   vt_out[(seg*vt_rows + (n - vt_col0)) * vt_ld + t],  seg = m / vt_T, t = m % vt_T
-  // which is the reference's V layout `[T, Dh, H]` per segment (1914-1920).
+  // columns n >= vt_col0 are written transposed (time contiguous) as F16: with nn = n - vt_col0,
+  //   vt_out[((seg*vt_heads + nn/64) * vt_head_rows + nn%64) * vt_ld + t],  seg = m / vt_T, t = m % vt_T
+  // which is the reference's V layout `[T, Dh, H]` per segment (1914-1920); each head block holds
+  // vt_head_rows >= 64 rows (the attention kernel keeps a row of ones after the 64 head rows).
   __half* vt_out = nullptr;
   int vt_col0 = 1 << 30;
-  int vt_rows = 0;
+  int vt_heads = 0;
+  int vt_head_rows = 64;
   int vt_ld = 0;
   int vt_T = 1;
   // swap-AB mode for skinny activations (decoder): the GEMM computes C^T; element (m, n) is
@@ -54,14 +56,17 @@ int gemm_pick_bn(int N);
 bool gemm_setup_attributes(const char** err);
 
 // ---- fused softmax attention (galois_flash_attn src/main.rs:1787-1797, call 1922) -------------
+constexpr int ATTN_VT_HEAD_ROWS = 80;   // 64 head rows + 1 row of ones + 15 zero rows (MMA N = 80)
 struct AttnProblem {
   CUtensorMap qk_map;  // dims {64, 2H, T, B} over the [B*T][2d] Q|K buffer, box {64,1,128,1}
-  CUtensorMap vt_map;  // dims {Tp, B*H*64} over V^T, box {64, 64}
+  CUtensorMap vt_map;  // dims {Tp, B*H*80} over V^T, box {64, 80}
   int B = 0, T = 0, H = 0;
   __half* out = nullptr;  // [B*T][H*64] merged heads (1924-1929)
   float scale = 0.125f;
+  long long* dbg = nullptr;  // optional clock64() trace buffer (1024 entries) for tools/prof_attention.py
 };
 cudaError_t launch_attention(const AttnProblem& a, cudaStream_t st);
+cudaError_t launch_vt_init(__half* vt, int n_heads_total, int Tp, cudaStream_t st);   // ones / zero rows
 bool attention_setup_attributes(const char** err);
 
 // ---- log-mel (src/main.rs:1554-1671) -----------------------------------------------------------
