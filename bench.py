@@ -49,7 +49,11 @@ def encoder_flops(hp) -> dict:
     d, L, Lt, T, nm = hp.n_audio_state, hp.n_audio_layer, hp.n_text_layer, hp.n_audio_ctx, hp.n_mels
     gemm = 2 * (2 * T) * d * 3 * nm + 2 * T * d * d * 3 + L * 24 * T * d * d + Lt * 4 * T * d * d
     attn = L * 4 * T * T * d
-    return {"gemm": float(gemm), "attention": float(attn), "total": float(gemm + attn)}
+    parts = {"gemm_conv1": 2 * (2 * T) * d * 3 * nm, "gemm_conv2": 2 * T * d * d * 3, "gemm_qkv": L * 6 * T * d * d,
+             "gemm_out": L * 2 * T * d * d, "gemm_fc1": L * 8 * T * d * d, "gemm_fc2": L * 8 * T * d * d,
+             "gemm_cross": Lt * 4 * T * d * d}
+    assert sum(parts.values()) == gemm
+    return {"gemm": float(gemm), "attention": float(attn), "total": float(gemm + attn), "parts": parts}
 
 
 def mel_bytes(hp, n_samples: int) -> float:
@@ -265,7 +269,8 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
     ctx.kernel_time_us("__reset__")
     ms_prof = timed(step_device, K)
     fam = {f: ctx.kernel_time_us(f) for f in ("gemm", "attention", "mel_frames", "mel_normalize", "mel_window",
-                                                "layernorm", "fill")}
+                                                "layernorm", "fill", "gemm_conv1", "gemm_conv2", "gemm_qkv",
+                                                "gemm_out", "gemm_fc1", "gemm_fc2", "gemm_cross")}
     ctx.kernel_time_us("__disable__")
 
     if rank == 0:
@@ -282,7 +287,10 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         mel_gbs = (mel_bytes(hp, n_samples) * B * K) / (mel_us * 1e-6) / 1e9 if mel_us else 0.0
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         step_us = ms_prof * 1e3 / K
-        shares = {k: (v[0] / K) / step_us for k, v in fam.items() if v[1]}
+        shares = {k: (v[0] / K) / step_us for k, v in fam.items() if v[1] and not k.startswith("gemm_")}
+        gemm_parts = {k: {"us_per_launch": fam[k][0] / fam[k][1], "launches_per_step": fam[k][1] / K,
+                          "tflops": fl["parts"][k] * B * K / (fam[k][0] * 1e-6) / 1e12}
+                      for k in fl["parts"] if fam[k][1]}
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -325,6 +333,7 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
                 "mel_frames": {"gbs": mel_gbs, "frac_of_hbm": mel_gbs / float(peaks["hbm_gbs"]),
                                "share_of_step": shares.get("mel_frames"), "bytes_per_segment": mel_bytes(hp, n_samples)},
                 "shares_of_step": shares,
+                "gemm_by_call_site": gemm_parts,
                 "whole_step_tflops": fl["total"] * B / (ms_dev / K * 1e-3) / 1e12,
                 "whole_step_frac_of_peak": fl["total"] * B / (ms_dev / K * 1e-3) / 1e12 / peak_tf,
             },

@@ -39,6 +39,8 @@ def test_layernorm(ctx):
 @pytest.mark.parametrize("M,N,K", [
     (128, 128, 64), (128, 256, 128), (300, 384, 384), (1500, 1152, 384), (257, 192, 240),
     (1000, 512, 2048), (96, 1536, 512), (130, 1000, 128), (64, 40, 64), (3000, 256, 240),
+    (6000, 1024, 256),    # more work items than CTA pairs: the persistent loop and both TMEM accumulators
+    (20000, 64, 64), (2050, 320, 128),
 ])
 def test_gemm_plain(ctx, M, N, K):
     from whisper_rs_b200 import api
@@ -52,10 +54,10 @@ def test_gemm_plain(ctx, M, N, K):
     assert np.abs(got16 - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
 
 
-def test_gemm_epilogues(ctx):
+@pytest.mark.parametrize("M,N,K", [(515, 768, 384), (9000, 512, 128), (300, 1280, 64)])
+def test_gemm_epilogues(ctx, M, N, K):
     from whisper_rs_b200 import api
     rng = np.random.default_rng(5)
-    M, N, K = 515, 768, 384
     a = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
     w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float16)
     bias = (0.3 * rng.standard_normal(N)).astype(np.float32)

@@ -1,0 +1,496 @@
+// gemm2.cu -- CTA-pair (tcgen05 cta_group::2) GEMM for the encoder's large-M products, sm_100a.
+//
+//   C[b][m][n] = epilogue( sum_k A[b][m][k] * W[n][k] )      f16 x f16 -> f32 accumulate (TMEM)
+//
+// Same call sites as gemm.cu (galois_matmul / galois_conv_1d_* of src/main.rs:1834, 1856,
+// 1891-1895, 1936, 1956, 1962, 1992, 2013 and the bias / scale / GELU / residual / F16-repack ops
+// that follow them); gemm.cu stays as the skinny swap-AB kernel of the decoder.
+//
+// Why a pair: a 128 x 256 tile per SM reads 48 KB of operands per 64-deep k-block, 96 B/clk of
+// L2->SM and shared-memory bandwidth at the tensor core's rate -- measured, that (and a
+// row-per-thread epilogue) capped the single-CTA kernel near 60 % tensor-pipe activity.  Here
+// two CTAs of one cluster own a 256 x BN tile: each loads its own 128 A rows and HALF of the W
+// tile (32 KB per k-block), one thread of the leader issues tcgen05.mma.cta_group::2 (M = 256),
+// and each CTA's TMEM receives its 128 accumulator rows.  The smaller stages leave shared memory
+// for a TMA-store epilogue.
+//
+// Roles per CTA (384 threads):
+//   warp 0      TMA producer (own A rows + own half of W; bytes counted on the LEADER's barrier)
+//   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts "stage free" and
+//               "accumulator ready" to both CTAs
+//   warp 2      TMEM allocator (2 x BN columns: the epilogue of tile i overlaps tile i+1's MMAs)
+//   warps 4-11  epilogue: tcgen05.ld (thread = row) -> bias / column scale / GELU / residual ->
+//               128-byte-swizzled shared-memory box -> cp.async.bulk.tensor store, so every
+//               global write (and the residual read, a TMA load prefetched one chunk ahead) is
+//               a full coalesced box and rows/columns past the tensor edge are clipped by the
+//               TMA unit.  The V^T scatter of the QKV projection keeps direct stores (lanes hold
+//               consecutive time steps, so those are coalesced already).
+#include "ptx.cuh"
+#include "wb_kernels.hpp"
+
+namespace wb {
+
+namespace {
+
+constexpr int BM = 128;            // accumulator rows per CTA (pair tile: 256)
+constexpr int BK = 64;             // one 128-byte swizzle atom of f16
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quarter, interleaved over column chunks
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 128 bytes (32 f32 or 64 f16 columns)
+constexpr int NBUF = 2;
+constexpr int STAGES = 4;
+
+struct Gemm2Args {
+  int M_rows, batch, N, K;
+  int m_pairs, n_tiles, total_items;
+  const float* bias;       // [N] or null
+  const float* colscale;   // [N] or null
+  float scale;
+  int gelu;
+  int out_f16;
+  int has_res;             // f32 residual tile fetched through res_map, added last
+  int res_bcast;           // residual has no batch dimension (positional embedding)
+  __half* vt_out;          // columns >= vt_col0 go to the transposed V buffer (see GemmEpilogue)
+  int vt_col0, vt_heads, vt_head_rows, vt_ld, vt_T;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_HALF_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * NBUF * EPI_BUF_BYTES;
+  static constexpr int BIAS_BYTES = EPI_WARPS * 2 * BN * 4;   // per warp: bias[BN], colscale[BN]
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(B_HALF_BYTES % 1024 == 0, "W half tile must keep the 1024-byte swizzle alignment");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB a CTA may use");
+};
+
+struct Item {
+  int b, mp, nt;
+};
+__device__ __forceinline__ Item item_coord(const Gemm2Args& a, int item) {
+  const int per_batch = a.m_pairs * a.n_tiles;
+  Item t;
+  t.b = item / per_batch;
+  const int r = item - t.b * per_batch;
+  t.mp = r / a.n_tiles;   // n fastest: pairs running concurrently share A rows through L2
+  t.nt = r - t.mp * a.n_tiles;
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
+                         const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap res_map,
+                         const Gemm2Args args) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_bufs = smem + C::RING_BYTES;
+  float* bias_stage = reinterpret_cast<float*>(epi_bufs + C::EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_stage) + C::BIAS_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]  (the leader's copy is the one in use)
+  uint64_t* res_bar = tmem_empty + 2;           // [EPI_WARPS][NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS * NBUF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&a_map);
+    prefetch_tmap(&w_map);
+    prefetch_tmap(&out_map);
+    if (args.has_res) prefetch_tmap(&res_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // the leader's arrive.expect_tx; both CTAs' TMA bytes land here
+      mbar_init(&empty_bar[s], 1);   // one multicast tcgen05.commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);   // every epilogue warp of both CTAs
+    }
+    for (int i = 0; i < EPI_WARPS * NBUF; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_cg2<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = (args.K + BK - 1) / BK;
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item0; item < args.total_items; item += item_step) {
+        const Item it = item_coord(args, item);
+        const int m0 = (it.mp * 2 + (int)rank) * BM;
+        const int n0 = it.nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);   // the pair's MMAs have drained this stage
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          tma_load_3d_cg2(sa, &a_map, full_leader, kb * BK, m0, it.b);
+          tma_load_2d_cg2(sa + A_BYTES, &w_map, full_leader, kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int item = item0; item < args.total_items; item += item_step, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_cg2(&empty_bar[stage], 3);
+          if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc], 3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // which interleaved half of the column chunks
+    uint8_t* my_bufs = epi_bufs + ew * NBUF * EPI_BUF_BYTES;
+    uint64_t* my_res_bar = res_bar + ew * NBUF;
+    float* my_bias = bias_stage + ew * 2 * BN;
+    float* my_cs = my_bias + BN;
+    const bool f16o = args.out_f16 != 0;
+    const int cw = f16o ? 64 : 32;                       // chunk width in columns (128 bytes of output)
+    const int n_chunks_tile = BN / cw;
+    const int my_nch = (n_chunks_tile - half + 1) / 2;   // chunks half, half+2, ...
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const bool has_cs = args.colscale != nullptr || args.scale != 1.0f;
+    const int sw = lane & 7;
+
+    // coordinates of this warp's chunk number `ci` (counted over all of its tiles)
+    auto chunk_coord = [&](int ci, int& n0, int& m0, int& b) -> bool {
+      const int t = ci / my_nch, k = ci - t * my_nch;
+      const int item = item0 + t * item_step;
+      if (item >= args.total_items) return false;
+      const Item it = item_coord(args, item);
+      n0 = it.nt * BN + (half + 2 * k) * cw;
+      m0 = (it.mp * 2 + (int)rank) * BM + q * 32;
+      b = it.b;
+      return true;
+    };
+    auto issue_residual = [&](int ci) {   // lane 0: TMA-load the f32 residual box of chunk ci into its buffer
+      int n0, m0, b;
+      if (!chunk_coord(ci, n0, m0, b)) return;
+      if (n0 >= args.N || n0 >= args.vt_col0) return;   // nothing will consume it (see the chunk loop)
+      const int buf = ci & (NBUF - 1);
+      mbar_arrive_expect_tx(&my_res_bar[buf], EPI_BUF_BYTES);
+      tma_load_3d(my_bufs + buf * EPI_BUF_BYTES, &res_map, &my_res_bar[buf], n0, m0, args.res_bcast ? 0 : b);
+    };
+
+    int ci = 0;   // chunks this warp has started
+    if (args.has_res && my_nch > 0 && lane == 0) issue_residual(0);
+    int t = 0;
+    for (int item = item0; item < args.total_items; item += item_step, ++t) {
+      const Item it = item_coord(args, item);
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      const int m_row0 = (it.mp * 2 + (int)rank) * BM + q * 32;
+      // ---- this tile's bias / column scale -> registers (issued before the accumulator wait)
+      constexpr int NV = (BN + 127) / 128;
+      float4 bb[NV], cc[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int j = v * 128 + lane * 4;
+        bb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cc[v] = make_float4(args.scale, args.scale, args.scale, args.scale);
+        if (j < BN && it.nt * BN + j < args.N) {
+          if (args.bias) bb[v] = __ldg(reinterpret_cast<const float4*>(args.bias + it.nt * BN + j));
+          if (args.colscale) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(args.colscale + it.nt * BN + j));
+            cc[v] = make_float4(c4.x * args.scale, c4.y * args.scale, c4.z * args.scale, c4.w * args.scale);
+          }
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the spin
+      tc_fence_after();
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int j = v * 128 + lane * 4;
+        if (j < BN) {
+          *reinterpret_cast<float4*>(my_bias + j) = bb[v];
+          *reinterpret_cast<float4*>(my_cs + j) = cc[v];
+        }
+      }
+      __syncwarp();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      if (my_nch == 0) {   // narrow tile: this warp has no chunk, but its arrival is counted
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+      }
+
+      for (int k = 0; k < my_nch; ++k, ++ci) {
+        const int c = half + 2 * k;            // chunk index inside the tile
+        const int col = c * cw;                // first accumulator column of the chunk
+        const int n0 = it.nt * BN + col;
+        const bool last_chunk = (k == my_nch - 1);
+        const bool dead = n0 >= args.N;        // ragged N: tile columns past the matrix
+        const bool to_vt = !dead && n0 >= args.vt_col0;
+        const int buf = ci & (NBUF - 1);
+        uint8_t* sbuf = my_bufs + buf * EPI_BUF_BYTES;
+        const uint32_t srow = smem_u32(sbuf) + lane * 128;
+
+        // ---- accumulator chunk -> registers
+        uint32_t r0[32], r1[32];
+        if (!dead) {
+          tmem_ld_32x32b_x32(t_row + col, r0);
+          if (f16o) tmem_ld_32x32b_x32(t_row + col + 32, r1);
+          tmem_ld_wait();
+        }
+        if (last_chunk) {   // this warp is done with the accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+        }
+        if (dead) continue;
+
+        // ---- bias, column scale, GELU (thread = row, registers = columns)
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(my_bias + col);
+          const float4* c4 = reinterpret_cast<const float4*>(my_cs + col);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bv = b4[g];
+            float x0 = __uint_as_float(r0[4 * g]) + bv.x, x1 = __uint_as_float(r0[4 * g + 1]) + bv.y;
+            float x2 = __uint_as_float(r0[4 * g + 2]) + bv.z, x3 = __uint_as_float(r0[4 * g + 3]) + bv.w;
+            if (has_cs) {
+              const float4 cv = c4[g];
+              x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+            }
+            if (args.gelu) {
+              x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
+            }
+            r0[4 * g] = __float_as_uint(x0); r0[4 * g + 1] = __float_as_uint(x1);
+            r0[4 * g + 2] = __float_as_uint(x2); r0[4 * g + 3] = __float_as_uint(x3);
+          }
+          if (f16o) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bv = b4[8 + g];
+              float x0 = __uint_as_float(r1[4 * g]) + bv.x, x1 = __uint_as_float(r1[4 * g + 1]) + bv.y;
+              float x2 = __uint_as_float(r1[4 * g + 2]) + bv.z, x3 = __uint_as_float(r1[4 * g + 3]) + bv.w;
+              if (has_cs) {
+                const float4 cv = c4[8 + g];
+                x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+              }
+              if (args.gelu) {
+                x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
+              }
+              r1[4 * g] = __float_as_uint(x0); r1[4 * g + 1] = __float_as_uint(x1);
+              r1[4 * g + 2] = __float_as_uint(x2); r1[4 * g + 3] = __float_as_uint(x3);
+            }
+          }
+        }
+
+        if (to_vt) {
+          // V^T scatter: time contiguous (reference layout [T, Dh, H], src/main.rs:1914-1920);
+          // lanes hold consecutive time steps, so each store instruction writes 64 contiguous bytes
+          const int m = m_row0 + lane;
+          if (m < args.M_rows) {
+            const int seg = m / args.vt_T;
+            const int tt = m - seg * args.vt_T;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int nn = n0 - args.vt_col0 + 32 * hh;   // multiple of 32: inside one head
+              __half* dst = args.vt_out +
+                            ((long long)(seg * args.vt_heads + (nn >> 6)) * args.vt_head_rows + (nn & 63)) * args.vt_ld + tt;
+              const uint32_t* rr = hh ? r1 : r0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[(long long)j * args.vt_ld] = __float2half_rn(__uint_as_float(rr[j]));
+            }
+          }
+          continue;
+        }
+
+        if (args.has_res) {
+          // ---- + residual: its box was TMA-loaded into this buffer one chunk ago
+          mbar_wait(&my_res_bar[buf], (ci / NBUF) & 1);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 x;
+            const uint32_t addr = srow + ((g ^ sw) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "r"(addr)
+                         : "memory");
+            x.x += __uint_as_float(r0[4 * g]); x.y += __uint_as_float(r0[4 * g + 1]);
+            x.z += __uint_as_float(r0[4 * g + 2]); x.w += __uint_as_float(r0[4 * g + 3]);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                         : "memory");
+          }
+        } else {
+          // the store that last read this buffer (chunk ci - NBUF) must have finished reading it
+          if (lane == 0) bulk_wait_group_read<NBUF - 1>();
+          __syncwarp();
+          if (f16o) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {   // 16-byte unit g = columns 8g .. 8g+7 of the 64-column chunk
+              const uint32_t* rr = (g < 4) ? r0 : r1;
+              const int o = (g & 3) * 8;
+              const uint32_t w0 = pack_h2(__uint_as_float(rr[o]), __uint_as_float(rr[o + 1]));
+              const uint32_t w1 = pack_h2(__uint_as_float(rr[o + 2]), __uint_as_float(rr[o + 3]));
+              const uint32_t w2 = pack_h2(__uint_as_float(rr[o + 4]), __uint_as_float(rr[o + 5]));
+              const uint32_t w3 = pack_h2(__uint_as_float(rr[o + 6]), __uint_as_float(rr[o + 7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ sw) << 4)), "r"(w0), "r"(w1),
+                           "r"(w2), "r"(w3)
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((g ^ sw) << 4)), "r"(r0[4 * g]),
+                           "r"(r0[4 * g + 1]), "r"(r0[4 * g + 2]), "r"(r0[4 * g + 3])
+                           : "memory");
+          }
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&out_map, sbuf, n0, m_row0, it.b);
+          bulk_commit_group();
+          if (args.has_res) {
+            // prefetch the next chunk's residual into the other buffer once the store that last
+            // read it (chunk ci - 1) has drained; the store just issued may stay in flight
+            bulk_wait_group_read<1>();
+            issue_residual(ci + 1);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the stores' reads
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA leaves while its peer may still read its shared memory / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN>, g.a_map, g.w_map, *g.out_map,
+                            g.res_map ? *g.res_map : *g.out_map, a);
+}
+
+template <int BN>
+bool set_attr(const char** err) {
+  cudaError_t e = cudaFuncSetAttribute(gemm2_f16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<BN>::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+bool gemm2_setup_attributes(const char** err) {
+  return set_attr<256>(err) && set_attr<192>(err) && set_attr<128>(err) && set_attr<64>(err);
+}
+
+// pair tile width: widest of 256 / 192 / 128 / 64 that divides N; 0 = not eligible (use gemm.cu)
+int gemm2_pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
+  if (!g.out_map || g.epi.transpose_out || gemm2_pick_bn(g.N) != g.bn) return cudaErrorInvalidValue;
+  Gemm2Args a;
+  a.M_rows = g.M_rows;
+  a.batch = g.batch;
+  a.N = g.N;
+  a.K = g.K;
+  a.m_pairs = (g.M_rows + 2 * BM - 1) / (2 * BM);
+  a.n_tiles = (g.N + g.bn - 1) / g.bn;
+  a.total_items = a.m_pairs * a.n_tiles * g.batch;
+  a.bias = g.epi.bias;
+  a.colscale = g.epi.colscale;
+  a.scale = g.epi.scale;
+  a.gelu = g.epi.gelu;
+  a.out_f16 = g.epi.out_f16;
+  a.has_res = g.res_map != nullptr;
+  a.res_bcast = g.res_bcast;
+  a.vt_out = g.epi.vt_out;
+  a.vt_col0 = g.epi.vt_col0;
+  a.vt_heads = g.epi.vt_heads;
+  a.vt_head_rows = g.epi.vt_head_rows;
+  a.vt_ld = g.epi.vt_ld;
+  a.vt_T = g.epi.vt_T;
+  if (a.total_items <= 0) return cudaSuccess;
+  const int max_pairs = num_sms / 2;
+  const int grid = 2 * (a.total_items < max_pairs ? a.total_items : max_pairs);
+  switch (g.bn) {
+    case 256: return launch_bn<256>(g, a, grid, st);
+    case 192: return launch_bn<192>(g, a, grid, st);
+    case 128: return launch_bn<128>(g, a, grid, st);
+    case 64: return launch_bn<64>(g, a, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace wb

@@ -44,8 +44,8 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const char** err) {
+static bool make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const char** err) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     *err = "cuTensorMapEncodeTiled not available (no CUDA driver?)";
@@ -60,7 +60,7 @@ bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i + 1 < rank) gs[i] = strides_bytes[i];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -72,6 +72,26 @@ bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return false;
   }
   return true;
+}
+
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const char** err) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, err);
+}
+bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const char** err) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, err);
+}
+
+// epilogue output / residual tensor of the pair GEMM: [batch][rows][N] with row stride ld and
+// batch stride bstride (elements); box = 128 bytes of columns x 32 rows
+bool tmap_out(CUtensorMap* m, const void* base, bool f32, uint64_t N, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+              uint64_t bstride_elems, const char** err) {
+  const uint64_t es = f32 ? 4 : 2;
+  const uint64_t dims[3] = {N, rows, batch};
+  const uint64_t st[2] = {ld_elems * es, (batch > 1 ? bstride_elems : rows * ld_elems) * es};
+  const uint32_t box[3] = {f32 ? 32u : 64u, 32, 1};
+  return f32 ? make_tmap_f32(m, base, 3, dims, st, box, err) : make_tmap_f16(m, base, 3, dims, st, box, err);
 }
 
 bool tmap_2d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
@@ -93,6 +113,11 @@ bool make_linear_maps(wb_ctx* ctx, Linear& l, bool want_a_map) {
   const char* err = "";
   l.bn = gemm_pick_bn(l.N);
   if (!tmap_2d_rows(&l.map_w, l.w, l.K, l.N, l.K, l.bn, &err)) {
+    fail_msg(ctx, WB_ERR_TENSOR_OP, err);
+    return false;
+  }
+  l.bn2 = want_a_map ? 0 : gemm2_pick_bn(l.N);   // encoder-side weights also get the pair kernel's half-tile map
+  if (l.bn2 && !tmap_2d_rows(&l.map_w2, l.w, l.K, l.N, l.K, l.bn2 / 2, &err)) {
     fail_msg(ctx, WB_ERR_TENSOR_OP, err);
     return false;
   }
@@ -156,21 +181,38 @@ void resolve_kernel_clocks(wb_ctx* ctx) {
   it->second.clear();
 }
 
+static bool force_gemm1() {
+  static const bool v = getenv("WB_GEMM1") != nullptr;   // developer aid: A/B the single-CTA kernel
+  return v;
+}
+
 int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const Linear& l, GemmEpilogue epi,
-             const char* family) {
+             const char* family, const CUtensorMap* out_map, const CUtensorMap* res_map, int res_bcast) {
   GemmProblem g;
   g.a_map = a_map;
-  g.w_map = l.map_w;
   g.M_rows = M_rows;
   g.batch = batch;
   g.N = l.N;
   g.K = l.K;
-  g.bn = l.bn;
   if (!epi.bias) epi.bias = l.bias;
   if (!epi.colscale) epi.colscale = l.colscale;
   g.epi = epi;
+  // pair kernel: needs the output (and residual) tensor maps; a residual needs whole tiles of f32 output
+  const bool pair = out_map && l.bn2 && !epi.transpose_out && !force_gemm1() && (!epi.residual || res_map) &&
+                    (!res_map || (!epi.out_f16 && l.N % l.bn2 == 0 && epi.vt_col0 >= l.N));
   LaunchTimer t(ctx, family);
-  WB_CK(launch_gemm(g, ctx->num_sms, ctx->stream));
+  if (pair) {
+    g.w_map = l.map_w2;
+    g.bn = l.bn2;
+    g.out_map = out_map;
+    g.res_map = epi.residual ? res_map : nullptr;
+    g.res_bcast = res_bcast;
+    WB_CK(launch_gemm2(g, ctx->num_sms, ctx->stream));
+  } else {
+    g.w_map = l.map_w;
+    g.bn = l.bn;
+    WB_CK(launch_gemm(g, ctx->num_sms, ctx->stream));
+  }
   return WB_OK;
 }
 
@@ -475,7 +517,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
   const char* aerr = "";
-  if (!gemm_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
+  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
     fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'kernel attribute setup: ") + aerr + "'");
     return bail(WB_ERR_TENSOR_OP);
   }
@@ -711,6 +753,15 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     const uint32_t box[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
     ok = make_tmap_f16(&ap.vt_map, ctx->vt, 2, dims, strd, box, &terr);
   }
+  // epilogue output / residual boxes of the pair GEMM
+  CUtensorMap o_conv1, o_x3, o_pe, o_x, o_qk, o_hid, o_cross;
+  ok = ok && tmap_out(&o_conv1, ctx->h1 + d, false, d, Tm, n_seg, d, (uint64_t)(Tm + 2) * d, &terr) &&
+       tmap_out(&o_x3, ctx->x, true, d, T, n_seg, d, (uint64_t)T * d, &terr) &&
+       tmap_out(&o_pe, ctx->e_pe, true, d, T, 1, d, 0, &terr) &&
+       tmap_out(&o_x, ctx->x, true, d, M, 1, d, 0, &terr) &&
+       tmap_out(&o_qk, ctx->qk, false, 2 * d, M, 1, 2 * d, 0, &terr) &&
+       tmap_out(&o_hid, ctx->hidden, false, 4 * d, M, 1, 4 * d, 0, &terr) &&
+       (Lt == 0 || tmap_out(&o_cross, ctx->cross, false, (uint64_t)Lt * 2 * d, M, 1, (uint64_t)Lt * 2 * d, 0, &terr));
   if (!ok) return fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
   ap.B = n_seg;
   ap.T = T;
@@ -743,7 +794,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     e.out_f16 = 1;
     e.out_bstride = (long long)(Tm + 2) * d;
     e.out_ld = d;
-    if ((rc = run_gemm(ctx, m_conv1, Tm, n_seg, ctx->conv1, e, "gemm_conv"))) return rc;
+    if ((rc = run_gemm(ctx, m_conv1, Tm, n_seg, ctx->conv1, e, "gemm_conv1", &o_conv1))) return rc;
     if (chk && (rc = probe_f16(1, ctx->h1 + d, Tm, d, d, (long long)(Tm + 2) * d))) return rc;
   }
   // E2 + E3: conv2 (stride 2) + bias + GELU, + positional embedding (1856-1875) -> residual stream
@@ -757,7 +808,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     e.out_f16 = 0;
     e.out_bstride = (long long)T * d;
     e.out_ld = d;
-    if ((rc = run_gemm(ctx, m_conv2, T, n_seg, ctx->conv2, e, "gemm_conv"))) return rc;
+    if ((rc = run_gemm(ctx, m_conv2, T, n_seg, ctx->conv2, e, "gemm_conv2", &o_x3, &o_pe, 1))) return rc;
     if (chk && (rc = probe_f32(2, ctx->x, (long long)T * d, (long long)T * d))) return rc;
   }
   for (int il = 0; il < L; ++il) {   // 1877-1975
@@ -777,7 +828,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.vt_head_rows = ATTN_VT_HEAD_ROWS;
       e.vt_ld = ctx->Tp;
       e.vt_T = T;
-      if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e))) return rc;
+      if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e, "gemm_qkv", &o_qk))) return rc;
     }
     {   // E7: flash attention + head merge (1922-1929)
       LaunchTimer t(ctx, "attention");
@@ -790,7 +841,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->x;
       e.out_f16 = 0;
       e.out_ld = d;
-      if ((rc = run_gemm(ctx, m_att, M, 1, l.out, e))) return rc;
+      if ((rc = run_gemm(ctx, m_att, M, 1, l.out, e, "gemm_out", &o_x, &o_x))) return rc;
     }
     {   // E9: mlp_ln, fc1 + bias + GELU, fc2 + bias + residual (1948-1968)
       LaunchTimer t(ctx, "layernorm");
@@ -802,7 +853,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->hidden;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
-      if ((rc = run_gemm(ctx, m_ln, M, 1, l.fc1, e))) return rc;
+      if ((rc = run_gemm(ctx, m_ln, M, 1, l.fc1, e, "gemm_fc1", &o_hid))) return rc;
     }
     {
       GemmEpilogue e;
@@ -811,7 +862,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->x;
       e.out_f16 = 0;
       e.out_ld = d;
-      if ((rc = run_gemm(ctx, m_hid, M, 1, l.fc2, e))) return rc;
+      if ((rc = run_gemm(ctx, m_hid, M, 1, l.fc2, e, "gemm_fc2", &o_x, &o_x))) return rc;
     }
     if (chk && (rc = probe_f32(3 + il, ctx->x, (long long)T * d, (long long)T * d))) return rc;
   }
@@ -825,7 +876,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     e.out = ctx->cross;
     e.out_f16 = 1;
     e.out_ld = Lt * 2 * d;
-    if ((rc = run_gemm(ctx, m_enc, M, 1, ctx->cross_kv, e, "gemm_cross"))) return rc;
+    if ((rc = run_gemm(ctx, m_enc, M, 1, ctx->cross_kv, e, "gemm_cross", &o_cross))) return rc;
     if (chk) {
       const long long ld = (long long)Lt * 2 * d;
       for (int il = 0; il < Lt; ++il) {
@@ -997,7 +1048,13 @@ int wb_dbg_gemm(wb_ctx* ctx, int M, int N, int K, const uint16_t* a_f16, const u
   ep.out = dO;
   ep.out_f16 = out_f16;
   ep.out_ld = N;
-  rc = run_gemm(ctx, ma, M, 1, l, ep, "dbg_gemm");
+  CUtensorMap mo, mr;
+  if (!tmap_out(&mo, dO, !out_f16, N, M, 1, N, 0, &terr) || (dR && !tmap_out(&mr, dR, true, N, M, 1, N, 0, &terr))) {
+    fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
+    cleanup();
+    return WB_ERR_TENSOR_OP;
+  }
+  rc = run_gemm(ctx, ma, M, 1, l, ep, "dbg_gemm", &mo, dR ? &mr : nullptr, 0);
   if (rc == WB_OK) {
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, WB_ERR_TENSOR_OP, "gemm kernel", e);

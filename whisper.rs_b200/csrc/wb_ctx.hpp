@@ -19,6 +19,8 @@ struct Linear {            // one weight matrix [N][K] f16 (row-major, K contigu
   CUtensorMap map_w;       // as the GEMM's W operand: dims {K, N}, box {64, bn}
   CUtensorMap map_a;       // as the A operand (swap-AB decode GEMMs): dims {K, N, 1}, box {64, 128, 1}
   bool has_map_a = false;
+  int bn2 = 0;             // pair-kernel tile width (gemm2.cu); 0 = not eligible
+  CUtensorMap map_w2;      // dims {K, N}, box {64, bn2 / 2}: each CTA of a pair loads half of the W tile
   const float* bias = nullptr;
   const float* colscale = nullptr;
 };

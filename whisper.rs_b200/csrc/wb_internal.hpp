@@ -49,8 +49,13 @@ bool tmap_3d_rows(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, u
                   uint64_t bstride_elems, const char** err);
 
 // run one Linear as C = A * W^T with the given A map / epilogue
+// out_map (+ res_map for an f32 residual) given: the CTA-pair kernel (gemm2.cu) runs it when the
+// shape is eligible; otherwise the single-CTA kernel with the pointers in `epi`
 int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const Linear& l, GemmEpilogue epi,
-             const char* family = "gemm");
+             const char* family = "gemm", const CUtensorMap* out_map = nullptr, const CUtensorMap* res_map = nullptr,
+             int res_bcast = 0);
+bool tmap_out(CUtensorMap* m, const void* base, bool f32, uint64_t N, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+              uint64_t bstride_elems, const char** err);
 
 // weight upload helpers (wb_api.cu)
 const HostTensor* find(const ModelFileView& mv, const std::string& n);

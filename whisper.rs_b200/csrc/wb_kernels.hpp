@@ -13,6 +13,9 @@ namespace wb {
 // f16 tensor, up to 4 dims; dims[0] innermost (contiguous); strides_bytes[i] = stride of dim i+1.
 bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const char** err);
+// same for an f32 tensor (epilogue output / residual boxes of gemm2.cu)
+bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, const char** err);
 
 // ---- GEMM: C[b][m][n] = epi( sum_k A[b][m][k] * W[n][k] ), f16 x f16 -> f32 (TMEM) -------------
 // Restates galois_matmul (src/main.rs:1752-1767) / galois_conv_1d_* (1709-1721) call sites with
@@ -50,10 +53,19 @@ struct GemmProblem {
   int M_rows = 0, batch = 1, N = 0, K = 0;
   int bn = 256;        // 32 | 64 | 128 | 192 | 256  (must match w_map's box)
   GemmEpilogue epi;
+  // ---- CTA-pair kernel (gemm2.cu) only: w_map box {64, bn/2}; the epilogue stores through out_map
+  // (dims {N, M_rows, batch}, box {64 f16 | 32 f32, 32, 1}, SWIZZLE_128B) and reads the f32 residual
+  // through res_map (same box shape; epi.residual is not used); res_bcast: residual has no batch dim
+  const CUtensorMap* out_map = nullptr;
+  const CUtensorMap* res_map = nullptr;
+  int res_bcast = 0;
 };
 cudaError_t launch_gemm(const GemmProblem& g, int num_sms, cudaStream_t st);
 int gemm_pick_bn(int N);
 bool gemm_setup_attributes(const char** err);
+cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st);
+int gemm2_pick_bn(int N);   // 0: N not eligible for the pair kernel
+bool gemm2_setup_attributes(const char** err);
 
 // ---- fused softmax attention (galois_flash_attn src/main.rs:1787-1797, call 1922) -------------
 constexpr int ATTN_VT_HEAD_ROWS = 80;   // 64 head rows + 1 row of ones + 15 zero rows (MMA N = 80)
