@@ -91,14 +91,21 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device = device
-        self.rows = []
+        self.rows = []      # (arrival time, csv line)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -106,12 +113,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -119,7 +126,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.03]
+        # the sampler starts before model load, so it is warm; a region shorter than one sampling period
+        # falls back to the samples closest to it (the last ones taken)
+        for r in (inside or [r for (_, r) in self.rows[-3:]]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -132,7 +142,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -201,6 +211,9 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
 
     arch, B, n_samples = args.arch, args.batch, args.samples
     hp = pkg.ggml_file.ARCHS[arch]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # early, so nvidia-smi is already streaming when the timed regions begin
     model = ensure_model(pkg, arch, rank, barrier)
     stream = torch.cuda.current_stream()
     ctx = api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples, device=local_rank,
@@ -248,9 +261,7 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         return ms
 
     # ---- timed region 1: device-resident inputs (value)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     l0 = ctx.timings()["n_kernel_launches"]
     ms_dev = timed(step_device, K)
     launches = ctx.timings()["n_kernel_launches"] - l0
@@ -263,6 +274,7 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, K)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 3: same K steps with per-launch CUDA events -> kernel-family device time
     ctx.kernel_time_us("__enable__")

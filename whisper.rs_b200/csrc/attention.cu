@@ -10,21 +10,28 @@
 //
 // One CTA = one (segment, head, 256-query block): two softmax warpgroups of 128 threads, each
 // owning one 128-query tile (thread r = query row r = TMEM lane r, so the row max needs no
-// cross-thread reduction), plus one control warp whose single elected thread issues every TMA
-// load and every tcgen05.mma.  Per 128-key tile j and warpgroup:
-//   S_j = Q K_j^T          tcgen05.mma 128 x 128 x 64  -> that warpgroup's TMEM columns [0,128)
-//   P_j = 2^(c S_j - m)    one TMEM pass into registers; exponentials split 2:1 between the MUFU
-//                          unit and an FMA-pipe polynomial (the MUFU alone would take twice the
-//                          tile's MMA time), packed to F16 into the swizzled K-major P tile
-//   O  += P_j [V_j | 1]    tcgen05.mma 128 x 80 x 128 accumulating in TMEM columns [128,208):
-//                          the V^T tile carries a row of ones after the 64 head rows, so column
-//                          64 of O is the softmax denominator, accumulated by the tensor core
+// cross-thread reduction), one warp that issues every tcgen05.mma (converged; one elected lane per
+// instruction) and one warp whose elected thread issues every TMA load.  Per 128-key tile j and
+// warpgroup:
+//   S_j = Q K_j^T          tcgen05.mma 128 x 128 x 64 -> that warpgroup's TMEM columns [0,128).
+//                          (N = 128 runs at the tensor pipe's rate; narrower tiles hit a ~47-cycle
+//                          floor per instruction, measured in tools/ubench/mma_rate.cu)
+//   P_j = 2^(c S_j - m)    one TMEM pass into registers (3-input FMNMX max); exponentials split
+//                          11 : 5 between the MUFU unit (16 / clk / SM -- alone it would take almost
+//                          twice the tile's MMA time) and an FMA-pipe polynomial; packed to F16 and
+//                          written BACK INTO TMEM over the first 64 columns of S (tcgen05.st), in two
+//                          64-key halves so that the first half's P.V runs under the second half's
+//                          exponentials
+//   O  += P_j [V_j | 1]    tcgen05.mma 128 x 80 x 128 with the A operand read from TMEM (no shared-
+//                          memory round trip for P); the V^T tile carries a row of ones after the 64
+//                          head rows, so column 64 of O is the softmax denominator, accumulated by
+//                          the tensor core from the same F16 probabilities
 // The output accumulator never leaves TMEM: the running max is applied lazily -- O is rescaled
 // (tcgen05.ld / tcgen05.st) only when a row's max grows by more than 2^8, which after the first
 // tiles is rare -- so the per-tile CUDA-core work is max + exp + pack only.
-// K_j / V_j stream through double-buffered TMA stages shared by both warpgroups (half the L2
-// traffic of one tile per CTA); all hand-offs are mbarriers (S ready, P ready, stage free), so
-// while one warpgroup's MMAs run the other warpgroup's softmax keeps the CUDA cores busy.
+// K_j / V_j stream through a 3-deep TMA ring shared by both warpgroups; all hand-offs are
+// mbarriers (S ready, P half ready x2, stage full / free), so while one warpgroup's MMAs run the
+// other warpgroup's softmax keeps the CUDA cores busy.
 #include "ptx.cuh"
 #include "wb_kernels.hpp"
 
@@ -33,257 +40,308 @@ namespace wb {
 namespace {
 
 constexpr int QT = 128;   // queries per softmax warpgroup
-constexpr int NWG = 2;    // query tiles (warpgroups) per CTA, sharing every K/V tile
-constexpr int KT = 128;   // keys per iteration
+constexpr int NWG = 2;    // query tiles (warpgroups) per CTA, sharing every K/V stage
+constexpr int KT = 128;   // keys per TMA stage
+constexpr int KS = 64;    // keys per step
 constexpr int DH = 64;
+constexpr int NS = 3;     // K/V stages
 constexpr int VROWS = ATTN_VT_HEAD_ROWS;          // 64 head rows + ones row + 15 zero rows
-constexpr int TILE_QK_BYTES = QT * DH * 2;        // 16 KB
+constexpr int TILE_QK_BYTES = QT * DH * 2;        // 16 KB: 128 rows of 128 bytes
 constexpr int TILE_V_HALF_BYTES = VROWS * 64 * 2; // 10 KB: [80 rows][64 keys]
 constexpr int TILE_V_BYTES = 2 * TILE_V_HALF_BYTES;
 constexpr int SMEM_Q = 0;                                      // NWG tiles
-constexpr int SMEM_K = SMEM_Q + NWG * TILE_QK_BYTES;           // 2 stages
-constexpr int SMEM_V = SMEM_K + 2 * TILE_QK_BYTES;             // 2 stages x 2 key halves
-constexpr int SMEM_P = SMEM_V + 2 * TILE_V_BYTES;              // NWG x 2 sub-tiles [128][64]
-constexpr int SMEM_BAR = SMEM_P + NWG * 2 * TILE_QK_BYTES;
-constexpr int ATTN_SMEM_BYTES = SMEM_BAR + 128;
-static_assert(SMEM_V % 1024 == 0 && SMEM_P % 1024 == 0 && TILE_V_HALF_BYTES % 1024 == 0, "swizzle alignment");
-constexpr int ATTN_THREADS = 32 * (4 * NWG + 1);  // softmax warpgroups + one control warp
+constexpr int SMEM_K = SMEM_Q + NWG * TILE_QK_BYTES;           // NS stages
+constexpr int SMEM_V = SMEM_K + NS * TILE_QK_BYTES;            // NS stages x 2 key halves
+constexpr int SMEM_XMAX = SMEM_V + NS * TILE_V_BYTES;            // [2][NWG][2 key halves][128 rows] f32
+constexpr int SMEM_BAR = SMEM_XMAX + 2 * NWG * 2 * QT * 4;   // double-buffered by step parity
+constexpr int ATTN_SMEM_BYTES = SMEM_BAR + 256;
+static_assert(SMEM_V % 1024 == 0 && TILE_V_HALF_BYTES % 1024 == 0, "swizzle alignment");
+constexpr int MMA_WARP = 8 * NWG, TMA_WARP = 8 * NWG + 1;   // after the 16 softmax warps
+constexpr int ATTN_THREADS = 32 * (8 * NWG + 2);
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_WG_STRIDE = 256;          // per warpgroup: S at +0 (128 cols), O at +128 (96 cols)
+constexpr uint32_t TMEM_WG_STRIDE = 256;          // per warpgroup: S buffers at +0 and +64 (P over them), O at +128
 constexpr uint32_t TMEM_S = 0, TMEM_O = 128;
 constexpr float RESCALE_LOG2 = 8.0f;              // lazy rescale threshold: P stays below 2^8
+// of every 16 exponentials, those whose index bit is set here run on the FMA pipe (5 of 16)
+constexpr uint32_t POLY_MASK16 = (1u << 1) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13);
 
 struct AttnArgs {
-  int B, T, H, n_kt;
+  int B, T, H, n_kt, n_steps;
   __half* out;
   float scale_log2;   // scale * log2(e)
-  long long* dbg;     // optional: clock64() trace of CTA (0,0,0) (tools/prof_attention.py); nullptr in production
+  long long* dbg;     // optional: clock64() trace of CTA (0,0,0) (tools/attn_trace.py); nullptr in production
 };
 #define ATTN_TRACE(slot)                                                          \
   do {                                                                            \
     if (trace) a.dbg[(slot)] = clock64();                                         \
   } while (0)
 
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
+// Lazy-rescale slow path: O[row][:] *= alpha for this thread's share of the accumulator columns
+// (head columns [32 hf, 32 hf + 32); hf == 0 also takes the denominator column 64 and the zero
+// columns behind it).  Rare after the first tiles, and deliberately NOT inlined: inlined, its 32
+// registers are live next to the 64 score registers and the steady-state loop spills.
+__device__ __noinline__ void rescale_o(uint32_t taddr_o, float alpha, int hf) {
+  {
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(taddr_o + hf * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_32x32b_x32(taddr_o + hf * 32, o);
+  }
+  if (hf == 0) {
+    uint32_t o[16];
+    tmem_ld_32x32b_x16(taddr_o + 64, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_32x32b_x16(taddr_o + 64, o);
+  }
+  tmem_st_wait();
+}
+
+// P for 32 keys: 2^(c s - m c) as F16 pairs, element i (and its pair i + 1) in register i / 2
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float moff, uint32_t (&p)[16]) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i0 = 2 * u, i1 = i0 + 1;
+    const float x0 = fmaf(__uint_as_float(s[i0]), c, -moff);
+    const float x1 = fmaf(__uint_as_float(s[i1]), c, -moff);
+    const float e0 = ((POLY_MASK16 >> (i0 & 15)) & 1u) ? ex2_fma(x0) : ex2_mufu(x0);
+    const float e1 = ((POLY_MASK16 >> (i1 & 15)) & 1u) ? ex2_fma(x1) : ex2_mufu(x1);
+    p[u] = pack_h2(e0, e1);
+  }
+}
+// max over 32 scores (3-input FMNMX, 4 independent chains)
+__device__ __forceinline__ float max_chunk(const uint32_t (&s)[32]) {
+  float m[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(__uint_as_float(s[u]), __uint_as_float(s[4 + u]), __uint_as_float(s[8 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(m[u], __uint_as_float(s[12 + u]), __uint_as_float(s[16 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(m[u], __uint_as_float(s[20 + u]), __uint_as_float(s[24 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmaxf(m[u], __uint_as_float(s[28 + u]));
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __grid_constant__ CUtensorMap vt_map,
                          const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);   // [NWG] Q tile landed
-  uint64_t* bar_k = bar_q + NWG;      // [2] K stage landed
-  uint64_t* bar_v = bar_k + 2;        // [2] V stage landed
-  uint64_t* bar_free = bar_v + 2;     // [2] MMAs of iteration parity retired: its K/V stages are reusable
-  uint64_t* bar_s = bar_free + 2;     // [NWG] S_j ready (and O accumulated through tile j-1)
-  uint64_t* bar_p = bar_s + NWG;      // [NWG] P_j written, S_j consumed (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + NWG);
+  uint64_t* bar_kfull = bar_q + NWG;        // [NS] K stage landed
+  uint64_t* bar_vfull = bar_kfull + NS;     // [NS] V stage landed
+  uint64_t* bar_free = bar_vfull + NS;      // [NS] every MMA reading the stage has retired
+  uint64_t* bar_s = bar_free + NS;          // [NWG][2] S buffer written
+  uint64_t* bar_p = bar_s + NWG * 2;        // [NWG][2] P written over the S buffer (256 arrivals)
+  uint64_t* bar_o = bar_p + NWG * 2;        // [NWG] P.V of the latest step retired: O is idle
+  uint64_t* bar_done = bar_o + NWG;         // [NWG] last P.V retired (single phase)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + NWG);
+  float* xmax = reinterpret_cast<float*>(smem + SMEM_XMAX);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int H = a.H, T = a.T, n_kt = a.n_kt;
+  const int H = a.H, T = a.T, n_kt = a.n_kt, n_steps = a.n_steps;
   const int q0 = blockIdx.x * (NWG * QT);   // first query of this CTA
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
     for (int i = 0; i < NWG; ++i) {
       mbar_init(&bar_q[i], 1);
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], QT);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_done[i], 1);
+      for (int k = 0; k < 2; ++k) {
+        mbar_init(&bar_s[i * 2 + k], 1);
+        mbar_init(&bar_p[i * 2 + k], 2 * QT);
+      }
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_k[i], 1);
-      mbar_init(&bar_v[i], 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bar_kfull[i], 1);
+      mbar_init(&bar_vfull[i], 1);
       mbar_init(&bar_free[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 4 * NWG) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4 * NWG) {
-    // ===================== control warp: every TMA load and every MMA, one thread =====================
+  if (warp == TMA_WARP) {
+    // ===================== TMA loads, one thread =====================
     if ((tid & 31) == 0) {
-      const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       prefetch_tmap(&qk_map);
       prefetch_tmap(&vt_map);
       const int vrow = (b * H + h) * VROWS;
-      auto load_k = [&](int j) {
-        const int st = j & 1;
-        mbar_arrive_expect_tx(&bar_k[st], TILE_QK_BYTES);
-        tma_load_4d(smem + SMEM_K + st * TILE_QK_BYTES, &qk_map, &bar_k[st], 0, H + h, j * KT, b);
-      };
-      auto load_v = [&](int j) {
-        const int st = j & 1;
-        mbar_arrive_expect_tx(&bar_v[st], TILE_V_BYTES);
-        tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES, &vt_map, &bar_v[st], j * KT, vrow);
-        tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES + TILE_V_HALF_BYTES, &vt_map, &bar_v[st], j * KT + 64, vrow);
-      };
-      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);      // 128 x 128
-      constexpr uint32_t idesc_o = umma_idesc_f16(QT, VROWS);   // 128 x 80
-      auto issue_s = [&](int wg, int j) {   // S_j[wg] = Q[wg] K_j^T
-        const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + SMEM_Q + wg * TILE_QK_BYTES));
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + SMEM_K + (j & 1) * TILE_QK_BYTES));
-        const uint32_t d = tmem_base + wg * TMEM_WG_STRIDE + TMEM_S;
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_f16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      };
-      auto issue_o = [&](int wg, int j) {   // O[wg] += P_j[wg] [V_j | 1]
-        const uint32_t pbase = smem_u32(smem + SMEM_P + wg * 2 * TILE_QK_BYTES);
-        const uint32_t vbase = smem_u32(smem + SMEM_V + (j & 1) * TILE_V_BYTES);
-        const uint64_t dp0 = umma_desc_k_sw128(pbase), dp1 = umma_desc_k_sw128(pbase + TILE_QK_BYTES);
-        const uint64_t dv0 = umma_desc_k_sw128(vbase), dv1 = umma_desc_k_sw128(vbase + TILE_V_HALF_BYTES);
-        const uint32_t d = tmem_base + wg * TMEM_WG_STRIDE + TMEM_O;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(d, dp0 + 2 * k, dv0 + 2 * k, idesc_o, (j | k) != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(d, dp1 + 2 * k, dv1 + 2 * k, idesc_o, 1);
-      };
       for (int wg = 0; wg < NWG; ++wg) {
         mbar_arrive_expect_tx(&bar_q[wg], TILE_QK_BYTES);
         tma_load_4d(smem + SMEM_Q + wg * TILE_QK_BYTES, &qk_map, &bar_q[wg], 0, h, q0 + wg * QT, b);
       }
-      load_k(0);
-      load_v(0);
-      if (n_kt > 1) {
-        load_k(1);
-        load_v(1);
-      }
-      mbar_wait(&bar_k[0], 0);
-      for (int wg = 0; wg < NWG; ++wg) {
-        mbar_wait(&bar_q[wg], 0);
-        tc_fence_after();
-        issue_s(wg, 0);
-        umma_commit(&bar_s[wg]);
-      }
       for (int j = 0; j < n_kt; ++j) {
-        // V_{j+1} goes into the stage P_{j-1} V_{j-1} read: reusable once iteration j-1's MMAs retired
-        if (j >= 1 && j + 1 < n_kt) {
-          mbar_wait(&bar_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          load_v(j + 1);
-        }
-        for (int wg = 0; wg < NWG; ++wg) {
-          ATTN_TRACE(512 + (j * 2 + wg) * 4 + 0);
-          mbar_wait(&bar_p[wg], j & 1);   // P_j[wg] in smem, S_j[wg] consumed
-          ATTN_TRACE(512 + (j * 2 + wg) * 4 + 1);
-          if (wg == 0) mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
-          tc_fence_after();
-          ATTN_TRACE(512 + (j * 2 + wg) * 4 + 2);
-          issue_o(wg, j);
-          if (j + 1 < n_kt) {
-            if (wg == 0) {
-              mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
-              tc_fence_after();
-            }
-            issue_s(wg, j + 1);
-          }
-          umma_commit(&bar_s[wg]);   // phase j+1 of this warpgroup
-          ATTN_TRACE(512 + (j * 2 + wg) * 4 + 3);
-        }
-        umma_commit(&bar_free[j & 1]);
-        // both warpgroups have consumed S_j (bar_p), so the MMAs that read K_j retired: refill its stage
-        if (j + 2 < n_kt) load_k(j + 2);
+        const int st = j % NS;
+        if (j >= NS) mbar_wait(&bar_free[st], ((j / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_kfull[st], TILE_QK_BYTES);
+        tma_load_4d(smem + SMEM_K + st * TILE_QK_BYTES, &qk_map, &bar_kfull[st], 0, H + h, j * KT, b);
+        mbar_arrive_expect_tx(&bar_vfull[st], TILE_V_BYTES);
+        tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES, &vt_map, &bar_vfull[st], j * KT, vrow);
+        tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES + TILE_V_HALF_BYTES, &vt_map, &bar_vfull[st], j * KT + 64, vrow);
       }
     }
+  } else if (warp == MMA_WARP) {
+    // ===================== every MMA: the whole warp runs this converged, one elected lane issues =====================
+    const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0;
+    constexpr uint32_t idesc_s = umma_idesc_f16(QT, KS);      // 128 x 64
+    constexpr uint32_t idesc_o = umma_idesc_f16(QT, VROWS);   // 128 x 80
+    const uint32_t q_addr = smem_u32(smem + SMEM_Q), k_addr = smem_u32(smem + SMEM_K), v_addr = smem_u32(smem + SMEM_V);
+    auto issue_s = [&](int wg, int j) {   // S_j[wg] = Q[wg] K_j^T  -> S buffer j & 1
+      const uint64_t dq = umma_desc_k_sw128(q_addr + wg * TILE_QK_BYTES);
+      const uint64_t dk = umma_desc_k_sw128(k_addr + ((j >> 1) % NS) * TILE_QK_BYTES + (j & 1) * (KS * 128));
+      const uint32_t d = tmem_base + wg * TMEM_WG_STRIDE + TMEM_S + (j & 1) * KS;
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_f16_ss_elect(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    };
+    auto issue_o = [&](int wg, int j) {   // O[wg] += P_j[wg] [V_j | 1]
+      const uint64_t dv = umma_desc_k_sw128(v_addr + ((j >> 1) % NS) * TILE_V_BYTES + (j & 1) * TILE_V_HALF_BYTES);
+      // P_j: keys [0,32) as 16 columns at the start of the S buffer, keys [32,64) as 16 columns at +32
+      const uint32_t pa = tmem_base + wg * TMEM_WG_STRIDE + TMEM_S + (j & 1) * KS;
+      const uint32_t d = tmem_base + wg * TMEM_WG_STRIDE + TMEM_O;
+#pragma unroll
+      for (int k = 0; k < KS / 16; ++k)
+        umma_f16_ts_elect(d, pa + (k >> 1) * 32 + (k & 1) * 8, dv + 2 * k, idesc_o, (j | k) != 0);
+    };
+    // prologue: the first two score tiles of each warpgroup
+    mbar_wait(&bar_kfull[0], 0);
+    for (int wg = 0; wg < NWG; ++wg) {
+      mbar_wait(&bar_q[wg], 0);
+      tc_fence_after();
+      issue_s(wg, 0);
+      umma_commit_elect(&bar_s[wg * 2 + 0]);
+      if (n_steps > 1) {
+        issue_s(wg, 1);
+        umma_commit_elect(&bar_s[wg * 2 + 1]);
+      }
+    }
+    for (int j = 0; j < n_steps; ++j) {
+      const int J = j >> 1, sb = j & 1;
+      for (int wg = 0; wg < NWG; ++wg) {
+        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 0);
+        mbar_wait(&bar_p[wg * 2 + sb], (j >> 1) & 1);   // P_j[wg] in TMEM, S_j[wg] consumed
+        if (wg == 0 && sb == 0) mbar_wait(&bar_vfull[J % NS], (J / NS) & 1);
+        tc_fence_after();
+        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 1);
+        issue_o(wg, j);
+        umma_commit_elect(&bar_o[wg]);
+        if (j == n_steps - 1) umma_commit_elect(&bar_done[wg]);
+        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 2);
+        if (j + 2 < n_steps) {
+          const int J2 = (j + 2) >> 1;
+          if (wg == 0 && sb == 0) {
+            mbar_wait(&bar_kfull[J2 % NS], (J2 / NS) & 1);
+            tc_fence_after();
+          }
+          issue_s(wg, j + 2);   // overwrites S_j / P_j: ordered behind the P.V MMAs above by the tensor pipe
+          umma_commit_elect(&bar_s[wg * 2 + sb]);
+        }
+        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 3);
+      }
+      // both halves of stage J have been read by every MMA issued so far: free once they retire
+      if (sb == 1 || j == n_steps - 1) umma_commit_elect(&bar_free[J % NS]);
+    }
   } else {
-    // ===================== softmax warpgroups: thread r owns query row r (TMEM lane r) =====================
-    const int wg = warp >> 2;
-    const int r = tid & (QT - 1);
-    const uint32_t twg = tmem_base + wg * TMEM_WG_STRIDE + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t p_row = smem_u32(smem + SMEM_P + wg * 2 * TILE_QK_BYTES) + r * 128;
-    const int sw = r & 7;
+    // ===================== softmax: 2 warpgroups x 8 warps; a thread owns HALF a query row =====================
+    // warp = g*8 + hf*4 + q: query tile g, key half hf (64 of the tile's 128 keys), TMEM lane quarter
+    // q (= warp % 4, the quarter the hardware lets this warp access); thread = row q*32 + lane.
+    // Four softmax warps per scheduler (not two) hide the MUFU / FMA latencies of the exponentials.
+    const int g = warp >> 3;
+    const int hf = (warp >> 2) & 1;
+    const int q = warp & 3;
+    const int lane = tid & 31;
+    const int r = q * 32 + lane;
+    const uint32_t twg = tmem_base + g * TMEM_WG_STRIDE + (uint32_t(q * 32) << 16);
+    float* my_max = xmax + (g * 2 + hf) * QT + r;          // this thread's half-row max (+ step parity * NWG*2*QT)
+    const float* peer_max = xmax + (g * 2 + (hf ^ 1)) * QT + r;
+    const int pair_bar = 1 + g * 4 + q;                    // the two warps that share these 32 rows
     const float c = a.scale_log2;
     float m_used = -INFINITY;   // row max (raw score units) the exponent offset currently refers to
-    const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0;
+    const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && hf == 0;
 
-    for (int j = 0; j < n_kt; ++j) {
-      ATTN_TRACE((j * 2 + wg) * 8 + 0);
-      mbar_wait(&bar_s[wg], j & 1);   // S_j ready; O accumulated through tile j-1 and idle
+    // one 64-key step; this thread takes 32 of the keys.  MASKED = the last step of the sequence
+    // (keys >= T get -inf); kept out of the steady-state instantiation: as a run-time test the
+    // compiler turns it into 3 predicated instructions per element on every step.
+    auto step = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const int sb = j & 1;
+      ATTN_TRACE((j * 2 + g) * 8 + 0);
+      mbar_wait(&bar_s[g * 2 + sb], (j >> 1) & 1);   // S_j ready (issued two steps ago: normally no wait)
       __syncwarp();
       tc_fence_after();
-      ATTN_TRACE((j * 2 + wg) * 8 + 1);
-      // ---- S row -> registers (one TMEM pass)
-      uint32_t s[KT];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-        tmem_ld_32x32b_x32(twg + TMEM_S + 0, s0);
-        tmem_ld_32x32b_x32(twg + TMEM_S + 32, s1);
-        tmem_ld_32x32b_x32(twg + TMEM_S + 64, s2);
-        tmem_ld_32x32b_x32(twg + TMEM_S + 96, s3);
-        tmem_ld_wait();
-      }
-      ATTN_TRACE((j * 2 + wg) * 8 + 2);
-      const int kbase = j * KT;
-      if (kbase + KT > T) {   // CTA-uniform; only the last key tile
+      ATTN_TRACE((j * 2 + g) * 8 + 1);
+      const uint32_t my_s = twg + TMEM_S + sb * KS + hf * 32;
+      uint32_t s[32];
+      tmem_ld_32x32b_x32(my_s, s);
+      tmem_ld_wait();
+      if (MASKED) {
+        const int kbase = j * KS + hf * 32;
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
+        for (int i = 0; i < 32; ++i)
           if (kbase + i >= T) s[i] = 0xff800000u;   // -inf: masked key
       }
-      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
-#pragma unroll
-      for (int i = 4; i < KT; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[i]));   // 4 independent chains
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      // ---- lazy running max: rescale O only when this row's max grew by more than 2^8
-      const bool grow = (mx - m_used) * c > RESCALE_LOG2;   // true on the first tile (m_used = -inf)
+      const float mxl = max_chunk(s);
+      ATTN_TRACE((j * 2 + g) * 8 + 2);
+      // ---- row max = max over both halves: exchange with the thread holding the other half
+      // (slots double-buffered by step parity: the next step's write cannot pass this step's read)
+      my_max[sb * (NWG * 2 * QT)] = mxl;
+      named_bar_sync(pair_bar, 64);
+      const float mx = fmaxf(mxl, peer_max[sb * (NWG * 2 * QT)]);
+      // ---- lazy running max: rescale O only when this row's max grew by more than 2^8 (both
+      // threads of a row see the same mx and m_used, so they decide alike)
+      const bool grow = (mx - m_used) * c > RESCALE_LOG2;   // true on the first step (m_used = -inf)
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        const float alpha = grow ? exp2f((m_used - mx) * c) : 1.0f;
-#pragma unroll 1
-        for (int cc = 0; cc < 3; ++cc) {   // columns [0,96) of O: 64 head values, denominator, zeros
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(twg + TMEM_O + cc * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(twg + TMEM_O + cc * 32, o);
-        }
-        tmem_st_wait();
+        mbar_wait(&bar_o[g], (j - 1) & 1);   // P_{j-1} V_{j-1} retired: O is idle until P_j is handed over
+        __syncwarp();
+        tc_fence_after();
+        rescale_o(twg + TMEM_O, grow ? exp2f((m_used - mx) * c) : 1.0f, hf);
       }
       if (grow) m_used = mx;
       const float moff = m_used * c;
-      ATTN_TRACE((j * 2 + wg) * 8 + 3);
-      // ---- P = 2^(c s - m c) -> F16 pairs straight into the swizzled K-major tile.  The MUFU unit
-      // (16 exp/clk/SM) would need 1024 cycles per 128 x 128 tile, twice the tile's MMA time, so every
-      // third exponential is evaluated on the FMA pipe instead (ex2_fma).
-#pragma unroll
-      for (int q16 = 0; q16 < KT / 8; ++q16) {   // 16-byte chunk q16 = keys [8 q16, 8 q16 + 8)
-        uint32_t w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i0 = 8 * q16 + 2 * u, i1 = i0 + 1;
-          const float x0 = fmaf(__uint_as_float(s[i0]), c, -moff);
-          const float x1 = fmaf(__uint_as_float(s[i1]), c, -moff);
-          const float e0 = (i0 % 3 == 0) ? ex2_fma(x0) : ex2_mufu(x0);
-          const float e1 = (i1 % 3 == 0) ? ex2_fma(x1) : ex2_mufu(x1);
-          w[u] = pack_h2(e0, e1);
-        }
-        const uint32_t addr = p_row + (q16 >> 3) * TILE_QK_BYTES + (((q16 & 7) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                     "r"(w[3])
-                     : "memory");
-      }
-      ATTN_TRACE((j * 2 + wg) * 8 + 4);
-      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
-      tc_fence_before();          // TMEM reads of S / writes of O ordered before the MMAs the control warp issues
-      mbar_arrive(&bar_p[wg]);
-      ATTN_TRACE((j * 2 + wg) * 8 + 5);
-    }
-    mbar_wait(&bar_s[wg], n_kt & 1);
+      ATTN_TRACE((j * 2 + g) * 8 + 3);
+      // ---- P = 2^(c s - m c) as F16 pairs (2 keys per column) over the first 16 of this thread's
+      // OWN 32 score columns
+      uint32_t p[16];
+      exp_chunk(s, c, moff, p);
+      tmem_st_32x32b_x16(my_s, p);
+      tmem_st_wait();
+      tc_fence_before();   // TMEM accesses ordered before the MMAs the MMA warp issues
+      mbar_arrive(&bar_p[g * 2 + sb]);
+      ATTN_TRACE((j * 2 + g) * 8 + 4);
+    };
+#pragma unroll 1
+    for (int j = 0; j < n_steps - 1; ++j) step(j, BoolTag<false>{});
+    if (n_steps * KS > T) step(n_steps - 1, BoolTag<true>{});
+    else step(n_steps - 1, BoolTag<false>{});
+    // (a parity wait on bar_o could be two phases behind here and return early: own barrier)
+    mbar_wait(&bar_done[g], 0);
     __syncwarp();
     tc_fence_after();
-    // ---- normalise and store merged heads: out[(b*T + t)][h*64 + c]  (permute + cpy, 1924-1929)
-    uint32_t o0[32], o1[32], o2[32];
-    tmem_ld_32x32b_x32(twg + TMEM_O, o0);
-    tmem_ld_32x32b_x32(twg + TMEM_O + 32, o1);
-    tmem_ld_32x32b_x32(twg + TMEM_O + 64, o2);
+    // ---- normalise and store merged heads: out[(b*T + t)][h*64 + c]  (permute + cpy, 1924-1929);
+    // this thread stores head columns [32 hf, 32 hf + 32)
+    uint32_t o0[32], o2[16];
+    tmem_ld_32x32b_x32(twg + TMEM_O + hf * 32, o0);
+    tmem_ld_32x32b_x16(twg + TMEM_O + 64, o2);
     tmem_ld_wait();
-    const int t = q0 + wg * QT + r;
+    const int t = q0 + g * QT + r;
     if (t < T) {
       const float inv = 1.0f / __uint_as_float(o2[0]);   // column 64: sum of the F16 probabilities
-      uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * T + t) * (H * DH) + h * DH);
+      uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * T + t) * (H * DH) + h * DH + hf * 32);
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {
         uint4 u;
@@ -293,20 +351,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
         u.w = pack_h2(__uint_as_float(o0[8 * q8 + 6]) * inv, __uint_as_float(o0[8 * q8 + 7]) * inv);
         dst[q8] = u;
       }
-#pragma unroll
-      for (int q8 = 0; q8 < 4; ++q8) {
-        uint4 u;
-        u.x = pack_h2(__uint_as_float(o1[8 * q8 + 0]) * inv, __uint_as_float(o1[8 * q8 + 1]) * inv);
-        u.y = pack_h2(__uint_as_float(o1[8 * q8 + 2]) * inv, __uint_as_float(o1[8 * q8 + 3]) * inv);
-        u.z = pack_h2(__uint_as_float(o1[8 * q8 + 4]) * inv, __uint_as_float(o1[8 * q8 + 5]) * inv);
-        u.w = pack_h2(__uint_as_float(o1[8 * q8 + 6]) * inv, __uint_as_float(o1[8 * q8 + 7]) * inv);
-        dst[4 + q8] = u;
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4 * NWG) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -346,6 +395,7 @@ cudaError_t launch_attention(const AttnProblem& p, cudaStream_t st) {
   a.T = p.T;
   a.H = p.H;
   a.n_kt = (p.T + KT - 1) / KT;
+  a.n_steps = (p.T + KS - 1) / KS;
   a.out = p.out;
   a.scale_log2 = p.scale * 1.4426950408889634f;
   a.dbg = p.dbg;
