@@ -232,11 +232,40 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         api.whisper_pcm_to_mel(ctx, devb[i % n_rot])
         api.whisper_encode(ctx, 1, offs, clip_ids=ids)
 
-    def step_e2e(i):
-        h = host[i % n_rot]
-        api.whisper_pcm_to_mel_ptr(ctx, h.data_ptr(), n_samples, B)   # H2D from pinned host memory inside
-        api.whisper_encode(ctx, 1, offs, clip_ids=ids)
-        return ctx.encoder_digest(B)                                   # D2H result read (syncs)
+    # ---- end-to-end leg: two contexts (each its own stream, staging buffers and activations) take
+    # alternate steps, so one step's host-side launches, H2D upload and D2H read-back overlap the other
+    # step's kernels -- the way a throughput server drives the library
+    ctx_b = api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples, device=local_rank,
+                                   decode_capacity=False)
+    e2e_ctx = [api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples,
+                                      device=local_rank, decode_capacity=False), ctx_b]
+
+    def e2e_submit(i):
+        cx, h = e2e_ctx[i % 2], host[i % n_rot]
+        api.whisper_pcm_to_mel_ptr(cx, h.data_ptr(), n_samples, B)   # H2D from pinned host memory (this step's input)
+        api.whisper_encode(cx, 1, offs, clip_ids=ids)
+
+    def e2e_collect(i):
+        return e2e_ctx[i % 2].encoder_digest(B)                      # D2H read of this step's result (syncs its stream)
+
+    def run_e2e(k):
+        """k steps, software-pipelined one deep: step i+1 is submitted before step i's result is read."""
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_submit(0)
+        for i in range(k):
+            if i + 1 < k:
+                e2e_submit(i + 1)
+            e2e_collect(i)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     W, K = max(3, args.warmup), max(1, args.steps)
     for i in range(W):
@@ -271,9 +300,8 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         dist.all_gather(g, torch.from_numpy(digests).to(dev))
         digests = torch.cat(g).cpu().numpy()
     # ---- timed region 2: end to end through the host-facing call
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, K)
+    run_e2e(4)   # warm-up (both contexts)
+    ms_e2e = run_e2e(K)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 3: same K steps with per-launch CUDA events -> kernel-family device time
@@ -324,6 +352,11 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
                 "sharding": "independent segments per rank, no data-path collective; one all_gather of digests",
                 "cache": f"per-step working set (~{(B * 1500 * hp.n_audio_state * 2 * (8 + 4 * hp.n_text_layer)) / 1e6:.0f} MB of "
                          f"activations) exceeds the 126 MB L2; PCM rotates over {n_rot} distinct batches",
+                "e2e_pipeline": "each e2e step = whisper_pcm_to_mel(pinned host PCM, H2D inside) + whisper_encode + "
+                                "encoder_digest read-back (D2H, syncs that context's stream); two contexts on their own "
+                                "streams take alternate steps and step i+1 is submitted before step i's result is read, "
+                                "so uploads, launches and read-backs overlap the other step's kernels; timed with the "
+                                "host clock between device-wide synchronisations (two streams), max over ranks",
                 "roofline_timing": "third timed pass of the same K steps with per-launch CUDA events on the launching stream",
             },
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * n_samples * 4,
@@ -354,6 +387,8 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         }
         print(json.dumps(out), flush=True)
     ctx.close()
+    for cx in e2e_ctx:
+        cx.close()
     if world > 1:
         dist.destroy_process_group()
 

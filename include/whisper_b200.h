@@ -85,6 +85,12 @@ int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips);
 int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, int n_clips);
 /* same with i16 PCM, the reference's real input: convert_integer_to_float_audio (1673-1679) */
 int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_clips);
+/* Start uploading the NEXT batch's host PCM (n_bytes of f32 or i16 samples, ideally pinned memory)
+ * on a separate copy stream while the current batch is still being encoded.  A following
+ * wb_pcm_to_mel / wb_pcm16_to_mel with the same pointer and byte count uses the uploaded copy
+ * instead of copying again.  The caller keeps the host buffer unchanged until that call.  (The
+ * reference holds its samples in an Arc<Vec<f32>> shared with its mel threads, 1584, 1681.) */
+int wb_pcm_prefetch(wb_ctx* ctx, const void* pcm, size_t n_bytes);
 int wb_mel_dims(const wb_ctx* ctx, int* n_mel, int* n_len, int* n_clips);
 int wb_mel_read(wb_ctx* ctx, int clip, float* out, size_t cap_floats);   /* [n_mel][n_len], layout of 1633 */
 int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clips); /* set ctx.mel directly */

@@ -80,3 +80,26 @@ def test_mel_device_resident_input(pkg, ctx):
     a = ctx.mel(0)
     api.whisper_pcm_to_mel(ctx, torch.from_numpy(pcm).cuda())
     np.testing.assert_array_equal(ctx.mel(0), a)
+
+
+def test_mel_prefetched_upload(pkg, ctx):
+    """wb_pcm_prefetch: the next batch's upload runs on the copy stream into the second staging
+    buffer; the following whisper_pcm_to_mel with the same host buffer must give the same mel as a
+    plain call, and a different buffer must fall back to an ordinary copy."""
+    from whisper_rs_b200 import api
+    a = np.ascontiguousarray(pkg.synth.make_segment(5, 160 * 500, 0.2))
+    b = np.ascontiguousarray(pkg.synth.make_segment(6, 160 * 500, 0.2))
+    api.whisper_pcm_to_mel(ctx, a)
+    ref_a = ctx.mel(0)
+    api.whisper_pcm_to_mel(ctx, b)
+    ref_b = ctx.mel(0)
+    for _ in range(3):   # alternate so both staging buffers are used as prefetch targets
+        api.whisper_pcm_prefetch_ptr(ctx, a.ctypes.data, a.nbytes)
+        api.whisper_pcm_to_mel_ptr(ctx, a.ctypes.data, a.size, 1)
+        np.testing.assert_array_equal(ctx.mel(0), ref_a)
+        api.whisper_pcm_prefetch_ptr(ctx, b.ctypes.data, b.nbytes)
+        api.whisper_pcm_to_mel_ptr(ctx, b.ctypes.data, b.size, 1)
+        np.testing.assert_array_equal(ctx.mel(0), ref_b)
+    api.whisper_pcm_prefetch_ptr(ctx, a.ctypes.data, a.nbytes)   # prefetched but not consumed ...
+    api.whisper_pcm_to_mel_ptr(ctx, b.ctypes.data, b.size, 1)    # ... a different buffer is copied normally
+    np.testing.assert_array_equal(ctx.mel(0), ref_b)

@@ -178,6 +178,12 @@ def whisper_pcm_to_mel_ptr(ctx: WhisperContext, host_ptr: int, n_samples: int, n
     _check(cabi.lib().wb_pcm_to_mel(ctx._h, host_ptr, n_samples, n_clips), ctx._h)
 
 
+def whisper_pcm_prefetch_ptr(ctx: WhisperContext, host_ptr: int, n_bytes: int) -> None:
+    """Begin the H2D upload of the NEXT batch (raw host pointer, pinned) on the context's copy stream;
+    the next whisper_pcm_to_mel* call with the same pointer uses it instead of copying again."""
+    _check(cabi.lib().wb_pcm_prefetch(ctx._h, host_ptr, n_bytes), ctx._h)
+
+
 def whisper_encode(ctx: WhisperContext, n_threads: int = 1, mel_offset=0,
                    clip_ids: Optional[Sequence[int]] = None) -> None:
     """src/main.rs:1799.  `n_threads` is accepted and ignored, as in the reference (1799, 2074).

@@ -10,28 +10,27 @@
 //
 // One CTA = one (segment, head, 256-query block): two softmax warpgroups of 128 threads, each
 // owning one 128-query tile (thread r = query row r = TMEM lane r, so the row max needs no
-// cross-thread reduction), one warp that issues every tcgen05.mma (converged; one elected lane per
-// instruction) and one warp whose elected thread issues every TMA load.  Per 128-key tile j and
-// warpgroup:
-//   S_j = Q K_j^T          tcgen05.mma 128 x 128 x 64 -> that warpgroup's TMEM columns [0,128).
-//                          (N = 128 runs at the tensor pipe's rate; narrower tiles hit a ~47-cycle
-//                          floor per instruction, measured in tools/ubench/mma_rate.cu)
+// cross-thread reduction), one warp that issues every tcgen05.mma (the warp stays converged; one
+// elected lane per instruction) and one warp whose elected thread issues every TMA load.  Keys
+// advance in steps of 64; per step j and warpgroup:
+//   S_j = Q K_j^T          tcgen05.mma 128 x 64 x 64 into one of TWO S buffers in TMEM, issued two
+//                          steps ahead, so the next scores are already there when a softmax ends
 //   P_j = 2^(c S_j - m)    one TMEM pass into registers (3-input FMNMX max); exponentials split
-//                          11 : 5 between the MUFU unit (16 / clk / SM -- alone it would take almost
-//                          twice the tile's MMA time) and an FMA-pipe polynomial; packed to F16 and
-//                          written BACK INTO TMEM over the first 64 columns of S (tcgen05.st), in two
-//                          64-key halves so that the first half's P.V runs under the second half's
-//                          exponentials
-//   O  += P_j [V_j | 1]    tcgen05.mma 128 x 80 x 128 with the A operand read from TMEM (no shared-
+//                          11 : 5 between the MUFU unit (16 / clk / SM -- alone it would take about
+//                          twice the step's MMA time) and an FMA-pipe polynomial; packed to F16 and
+//                          written BACK INTO TMEM over the S buffer just consumed (tcgen05.st)
+//   O  += P_j [V_j | 1]    tcgen05.mma 128 x 80 x 64 with the A operand read from TMEM (no shared-
 //                          memory round trip for P); the V^T tile carries a row of ones after the 64
 //                          head rows, so column 64 of O is the softmax denominator, accumulated by
 //                          the tensor core from the same F16 probabilities
 // The output accumulator never leaves TMEM: the running max is applied lazily -- O is rescaled
-// (tcgen05.ld / tcgen05.st) only when a row's max grows by more than 2^8, which after the first
-// tiles is rare -- so the per-tile CUDA-core work is max + exp + pack only.
-// K_j / V_j stream through a 3-deep TMA ring shared by both warpgroups; all hand-offs are
-// mbarriers (S ready, P half ready x2, stage full / free), so while one warpgroup's MMAs run the
-// other warpgroup's softmax keeps the CUDA cores busy.
+// (tcgen05.ld / tcgen05.st, after waiting for the previous P.V to retire) only when a row's max
+// grows by more than 2^8, which after the first steps is rare.
+// K / V^T arrive as 128-key stages (a stage serves two steps) through a 3-deep TMA ring shared by
+// both warpgroups; every hand-off is an mbarrier (S ready x2, P ready x2, O idle, stage full /
+// free).  Measured constraints behind the shape (tools/ubench): a tcgen05.mma of M = 128 costs
+// max(~47, N/2) cycles, so the 64- and 80-wide tiles run at the instruction floor; FMNMX3 costs the
+// same as FMNMX; ex2.approx.f16x2 gives no MUFU throughput over the f32 form.
 #include "ptx.cuh"
 #include "wb_kernels.hpp"
 
@@ -52,12 +51,11 @@ constexpr int TILE_V_BYTES = 2 * TILE_V_HALF_BYTES;
 constexpr int SMEM_Q = 0;                                      // NWG tiles
 constexpr int SMEM_K = SMEM_Q + NWG * TILE_QK_BYTES;           // NS stages
 constexpr int SMEM_V = SMEM_K + NS * TILE_QK_BYTES;            // NS stages x 2 key halves
-constexpr int SMEM_XMAX = SMEM_V + NS * TILE_V_BYTES;            // [2][NWG][2 key halves][128 rows] f32
-constexpr int SMEM_BAR = SMEM_XMAX + 2 * NWG * 2 * QT * 4;   // double-buffered by step parity
+constexpr int SMEM_BAR = SMEM_V + NS * TILE_V_BYTES;
 constexpr int ATTN_SMEM_BYTES = SMEM_BAR + 256;
 static_assert(SMEM_V % 1024 == 0 && TILE_V_HALF_BYTES % 1024 == 0, "swizzle alignment");
-constexpr int MMA_WARP = 8 * NWG, TMA_WARP = 8 * NWG + 1;   // after the 16 softmax warps
-constexpr int ATTN_THREADS = 32 * (8 * NWG + 2);
+constexpr int MMA_WARP = 4 * NWG, TMA_WARP = 4 * NWG + 1;   // after the 8 softmax warps
+constexpr int ATTN_THREADS = 32 * (4 * NWG + 2);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_WG_STRIDE = 256;          // per warpgroup: S buffers at +0 and +64 (P over them), O at +128
 constexpr uint32_t TMEM_S = 0, TMEM_O = 128;
@@ -81,26 +79,19 @@ struct BoolTag {
   static constexpr bool value = B;
 };
 
-// Lazy-rescale slow path: O[row][:] *= alpha for this thread's share of the accumulator columns
-// (head columns [32 hf, 32 hf + 32); hf == 0 also takes the denominator column 64 and the zero
-// columns behind it).  Rare after the first tiles, and deliberately NOT inlined: inlined, its 32
-// registers are live next to the 64 score registers and the steady-state loop spills.
-__device__ __noinline__ void rescale_o(uint32_t taddr_o, float alpha, int hf) {
-  {
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(taddr_o + hf * 32, o);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-    tmem_st_32x32b_x32(taddr_o + hf * 32, o);
-  }
-  if (hf == 0) {
+
+// Lazy-rescale slow path: O[row][:] *= alpha over the accumulator's 80 columns (64 head values, the
+// denominator, zeros).  Rare after the first steps, and deliberately NOT inlined: inlined, its
+// registers are live next to the score registers of the steady-state loop.
+__device__ __noinline__ void rescale_o(uint32_t taddr_o, float alpha) {
+#pragma unroll 1
+  for (int cc = 0; cc < 5; ++cc) {
     uint32_t o[16];
-    tmem_ld_32x32b_x16(taddr_o + 64, o);
+    tmem_ld_32x32b_x16(taddr_o + cc * 16, o);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-    tmem_st_32x32b_x16(taddr_o + 64, o);
+    tmem_st_32x32b_x16(taddr_o + cc * 16, o);
   }
   tmem_st_wait();
 }
@@ -144,7 +135,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
   uint64_t* bar_o = bar_p + NWG * 2;        // [NWG] P.V of the latest step retired: O is idle
   uint64_t* bar_done = bar_o + NWG;         // [NWG] last P.V retired (single phase)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + NWG);
-  float* xmax = reinterpret_cast<float*>(smem + SMEM_XMAX);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -160,7 +150,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       mbar_init(&bar_done[i], 1);
       for (int k = 0; k < 2; ++k) {
         mbar_init(&bar_s[i * 2 + k], 1);
-        mbar_init(&bar_p[i * 2 + k], 2 * QT);
+        mbar_init(&bar_p[i * 2 + k], QT);
       }
     }
     for (int i = 0; i < NS; ++i) {
@@ -211,12 +201,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     };
     auto issue_o = [&](int wg, int j) {   // O[wg] += P_j[wg] [V_j | 1]
       const uint64_t dv = umma_desc_k_sw128(v_addr + ((j >> 1) % NS) * TILE_V_BYTES + (j & 1) * TILE_V_HALF_BYTES);
-      // P_j: keys [0,32) as 16 columns at the start of the S buffer, keys [32,64) as 16 columns at +32
-      const uint32_t pa = tmem_base + wg * TMEM_WG_STRIDE + TMEM_S + (j & 1) * KS;
+      const uint32_t pa = tmem_base + wg * TMEM_WG_STRIDE + TMEM_S + (j & 1) * KS;   // P_j: 64 F16 = 32 columns
       const uint32_t d = tmem_base + wg * TMEM_WG_STRIDE + TMEM_O;
 #pragma unroll
-      for (int k = 0; k < KS / 16; ++k)
-        umma_f16_ts_elect(d, pa + (k >> 1) * 32 + (k & 1) * 8, dv + 2 * k, idesc_o, (j | k) != 0);
+      for (int k = 0; k < KS / 16; ++k) umma_f16_ts_elect(d, pa + 8 * k, dv + 2 * k, idesc_o, (j | k) != 0);
     };
     // prologue: the first two score tiles of each warpgroup
     mbar_wait(&bar_kfull[0], 0);
@@ -257,26 +245,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       if (sb == 1 || j == n_steps - 1) umma_commit_elect(&bar_free[J % NS]);
     }
   } else {
-    // ===================== softmax: 2 warpgroups x 8 warps; a thread owns HALF a query row =====================
-    // warp = g*8 + hf*4 + q: query tile g, key half hf (64 of the tile's 128 keys), TMEM lane quarter
-    // q (= warp % 4, the quarter the hardware lets this warp access); thread = row q*32 + lane.
-    // Four softmax warps per scheduler (not two) hide the MUFU / FMA latencies of the exponentials.
-    const int g = warp >> 3;
-    const int hf = (warp >> 2) & 1;
-    const int q = warp & 3;
-    const int lane = tid & 31;
-    const int r = q * 32 + lane;
-    const uint32_t twg = tmem_base + g * TMEM_WG_STRIDE + (uint32_t(q * 32) << 16);
-    float* my_max = xmax + (g * 2 + hf) * QT + r;          // this thread's half-row max (+ step parity * NWG*2*QT)
-    const float* peer_max = xmax + (g * 2 + (hf ^ 1)) * QT + r;
-    const int pair_bar = 1 + g * 4 + q;                    // the two warps that share these 32 rows
+    // ===================== softmax warpgroups: thread r owns query row r (TMEM lane r) =====================
+    const int g = warp >> 2;
+    const int r = tid & (QT - 1);
+    const uint32_t twg = tmem_base + g * TMEM_WG_STRIDE + (uint32_t((warp & 3) * 32) << 16);
     const float c = a.scale_log2;
     float m_used = -INFINITY;   // row max (raw score units) the exponent offset currently refers to
-    const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && hf == 0;
+    const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0;
 
-    // one 64-key step; this thread takes 32 of the keys.  MASKED = the last step of the sequence
-    // (keys >= T get -inf); kept out of the steady-state instantiation: as a run-time test the
-    // compiler turns it into 3 predicated instructions per element on every step.
+    // one 64-key step.  MASKED = the last step of the sequence (keys >= T get -inf); kept out of the
+    // steady-state instantiation: as a run-time test the compiler turns it into 3 predicated
+    // instructions per element on every step.
+    // (Tried and measured slower or equal on B200, see DESIGN.md: 16 softmax warps with half a row per
+    // thread; software-pipelining the next step's TMEM load and max under the exponentials.)
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int sb = j & 1;
@@ -285,40 +266,41 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       __syncwarp();
       tc_fence_after();
       ATTN_TRACE((j * 2 + g) * 8 + 1);
-      const uint32_t my_s = twg + TMEM_S + sb * KS + hf * 32;
-      uint32_t s[32];
-      tmem_ld_32x32b_x32(my_s, s);
+      const uint32_t my_s = twg + TMEM_S + sb * KS;
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(my_s, s0);
+      tmem_ld_32x32b_x32(my_s + 32, s1);
       tmem_ld_wait();
       if (MASKED) {
-        const int kbase = j * KS + hf * 32;
+        const int kbase = j * KS;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + i >= T) s[i] = 0xff800000u;   // -inf: masked key
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i >= T) s0[i] = 0xff800000u;   // -inf: masked key
+          if (kbase + 32 + i >= T) s1[i] = 0xff800000u;
+        }
       }
-      const float mxl = max_chunk(s);
+      const float mx = fmaxf(max_chunk(s0), max_chunk(s1));
       ATTN_TRACE((j * 2 + g) * 8 + 2);
-      // ---- row max = max over both halves: exchange with the thread holding the other half
-      // (slots double-buffered by step parity: the next step's write cannot pass this step's read)
-      my_max[sb * (NWG * 2 * QT)] = mxl;
-      named_bar_sync(pair_bar, 64);
-      const float mx = fmaxf(mxl, peer_max[sb * (NWG * 2 * QT)]);
-      // ---- lazy running max: rescale O only when this row's max grew by more than 2^8 (both
-      // threads of a row see the same mx and m_used, so they decide alike)
+      // ---- lazy running max: rescale O only when this row's max grew by more than 2^8
       const bool grow = (mx - m_used) * c > RESCALE_LOG2;   // true on the first step (m_used = -inf)
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         mbar_wait(&bar_o[g], (j - 1) & 1);   // P_{j-1} V_{j-1} retired: O is idle until P_j is handed over
         __syncwarp();
         tc_fence_after();
-        rescale_o(twg + TMEM_O, grow ? exp2f((m_used - mx) * c) : 1.0f, hf);
+        rescale_o(twg + TMEM_O, grow ? exp2f((m_used - mx) * c) : 1.0f);
       }
       if (grow) m_used = mx;
       const float moff = m_used * c;
       ATTN_TRACE((j * 2 + g) * 8 + 3);
-      // ---- P = 2^(c s - m c) as F16 pairs (2 keys per column) over the first 16 of this thread's
-      // OWN 32 score columns
-      uint32_t p[16];
-      exp_chunk(s, c, moff, p);
-      tmem_st_32x32b_x16(my_s, p);
+      // ---- P = 2^(c s - m c) as F16 pairs (2 keys per column) over the first 32 columns of the S
+      // buffer just read
+      {
+        uint32_t p[16];
+        exp_chunk(s0, c, moff, p);
+        tmem_st_32x32b_x16(my_s, p);
+        exp_chunk(s1, c, moff, p);
+        tmem_st_32x32b_x16(my_s + 16, p);
+      }
       tmem_st_wait();
       tc_fence_before();   // TMEM accesses ordered before the MMAs the MMA warp issues
       mbar_arrive(&bar_p[g * 2 + sb]);
@@ -332,16 +314,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     mbar_wait(&bar_done[g], 0);
     __syncwarp();
     tc_fence_after();
-    // ---- normalise and store merged heads: out[(b*T + t)][h*64 + c]  (permute + cpy, 1924-1929);
-    // this thread stores head columns [32 hf, 32 hf + 32)
-    uint32_t o0[32], o2[16];
-    tmem_ld_32x32b_x32(twg + TMEM_O + hf * 32, o0);
+    // ---- normalise and store merged heads: out[(b*T + t)][h*64 + c]  (permute + cpy, 1924-1929)
+    uint32_t o0[32], o1[32], o2[16];
+    tmem_ld_32x32b_x32(twg + TMEM_O, o0);
+    tmem_ld_32x32b_x32(twg + TMEM_O + 32, o1);
     tmem_ld_32x32b_x16(twg + TMEM_O + 64, o2);
     tmem_ld_wait();
     const int t = q0 + g * QT + r;
     if (t < T) {
       const float inv = 1.0f / __uint_as_float(o2[0]);   // column 64: sum of the F16 probabilities
-      uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * T + t) * (H * DH) + h * DH + hf * 32);
+      uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * T + t) * (H * DH) + h * DH);
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {
         uint4 u;
@@ -350,6 +332,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
         u.z = pack_h2(__uint_as_float(o0[8 * q8 + 4]) * inv, __uint_as_float(o0[8 * q8 + 5]) * inv);
         u.w = pack_h2(__uint_as_float(o0[8 * q8 + 6]) * inv, __uint_as_float(o0[8 * q8 + 7]) * inv);
         dst[q8] = u;
+      }
+#pragma unroll
+      for (int q8 = 0; q8 < 4; ++q8) {
+        uint4 u;
+        u.x = pack_h2(__uint_as_float(o1[8 * q8 + 0]) * inv, __uint_as_float(o1[8 * q8 + 1]) * inv);
+        u.y = pack_h2(__uint_as_float(o1[8 * q8 + 2]) * inv, __uint_as_float(o1[8 * q8 + 3]) * inv);
+        u.z = pack_h2(__uint_as_float(o1[8 * q8 + 4]) * inv, __uint_as_float(o1[8 * q8 + 5]) * inv);
+        u.w = pack_h2(__uint_as_float(o1[8 * q8 + 6]) * inv, __uint_as_float(o1[8 * q8 + 7]) * inv);
+        dst[4 + q8] = u;
       }
     }
   }

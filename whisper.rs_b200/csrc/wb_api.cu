@@ -414,9 +414,15 @@ int alloc_activations(wb_ctx* ctx) {
   ctx->d_mel_floats = (size_t)ctx->cfg.max_clips * ctx->mel_tab.n_mel * (max_len ? max_len : 1);
   if ((rc = dev_alloc(ctx, &ctx->d_mel, ctx->d_mel_floats))) return rc;
   ctx->d_pcm_bytes = (size_t)ctx->cfg.max_clips * (size_t)ctx->cfg.max_clip_samples * 4;
-  uint8_t* pcm = nullptr;
-  if ((rc = dev_alloc(ctx, &pcm, ctx->d_pcm_bytes, false))) return rc;
-  ctx->d_pcm = pcm;
+  for (int i = 0; i < 2; ++i) {
+    uint8_t* pcm = nullptr;
+    if ((rc = dev_alloc(ctx, &pcm, ctx->d_pcm_bytes, false))) return rc;
+    ctx->d_pcm_buf[i] = pcm;
+    WB_CK(cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
+    WB_CK(cudaEventCreateWithFlags(&ctx->ev_mel_read[i], cudaEventDisableTiming));
+  }
+  ctx->d_pcm = ctx->d_pcm_buf[0];
+  WB_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if ((rc = dev_alloc(ctx, &ctx->d_clip_max, (size_t)ctx->cfg.max_clips))) return rc;
   return WB_OK;
 }
@@ -590,6 +596,14 @@ void wb_ctx_free(wb_ctx* ctx) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
+    if (ctx->ev_mel_read[i]) cudaEventDestroy(ctx->ev_mel_read[i]);
+  }
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -651,24 +665,56 @@ int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, in
   return mel_run(ctx, pcm_dev, 0, n_samples, n_clips);
 }
 
-int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips) {
-  if (!ctx || !pcm) return WB_ERR_UNEXPECTED;
-  cudaSetDevice(ctx->device);
-  const size_t bytes = (size_t)n_clips * n_samples * 4;
-  if (n_clips < 1 || bytes > ctx->d_pcm_bytes)
+// host PCM -> the staging buffer the mel kernel reads.  If wb_pcm_prefetch already uploaded exactly
+// these bytes into the other buffer, switch to it and only wait for that copy.
+static int stage_host_pcm(wb_ctx* ctx, const void* pcm, size_t bytes) {
+  if (bytes > ctx->d_pcm_bytes)
     return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
-  WB_CK(cudaMemcpyAsync(ctx->d_pcm, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return mel_run(ctx, ctx->d_pcm, 0, n_samples, n_clips);
+  const int other = ctx->pcm_cur ^ 1;
+  if (ctx->pf_host[other] == pcm && ctx->pf_bytes[other] == bytes) {
+    ctx->pcm_cur = other;
+    ctx->pf_host[other] = nullptr;
+    WB_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[other], 0));
+  } else {
+    WB_CK(cudaMemcpyAsync(ctx->d_pcm_buf[ctx->pcm_cur], pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->d_pcm = ctx->d_pcm_buf[ctx->pcm_cur];
+  return WB_OK;
+}
+
+int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips) {
+  if (!ctx || !pcm || n_clips < 1) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  int rc = stage_host_pcm(ctx, pcm, (size_t)n_clips * n_samples * 4);
+  if (rc) return rc;
+  rc = mel_run(ctx, ctx->d_pcm, 0, n_samples, n_clips);
+  if (rc == WB_OK) WB_CK(cudaEventRecord(ctx->ev_mel_read[ctx->pcm_cur], ctx->stream));
+  return rc;
 }
 
 int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_clips) {
+  if (!ctx || !pcm || n_clips < 1) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  int rc = stage_host_pcm(ctx, pcm, (size_t)n_clips * n_samples * 2);
+  if (rc) return rc;
+  rc = mel_run(ctx, ctx->d_pcm, 1, n_samples, n_clips);
+  if (rc == WB_OK) WB_CK(cudaEventRecord(ctx->ev_mel_read[ctx->pcm_cur], ctx->stream));
+  return rc;
+}
+
+int wb_pcm_prefetch(wb_ctx* ctx, const void* pcm, size_t n_bytes) {
   if (!ctx || !pcm) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const size_t bytes = (size_t)n_clips * n_samples * 2;
-  if (n_clips < 1 || bytes > ctx->d_pcm_bytes)
+  if (n_bytes > ctx->d_pcm_bytes)
     return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
-  WB_CK(cudaMemcpyAsync(ctx->d_pcm, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return mel_run(ctx, ctx->d_pcm, 1, n_samples, n_clips);
+  const int other = ctx->pcm_cur ^ 1;
+  // the mel kernel that last read this buffer must have finished before it is overwritten
+  WB_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_mel_read[other], 0));
+  WB_CK(cudaMemcpyAsync(ctx->d_pcm_buf[other], pcm, n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  WB_CK(cudaEventRecord(ctx->ev_copy_done[other], ctx->copy_stream));
+  ctx->pf_host[other] = pcm;
+  ctx->pf_bytes[other] = n_bytes;
+  return WB_OK;
 }
 
 int wb_mel_dims(const wb_ctx* ctx, int* n_mel, int* n_len, int* n_clips) {

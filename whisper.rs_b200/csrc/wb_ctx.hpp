@@ -69,8 +69,17 @@ struct wb_ctx {
 
   // ---- mel
   wb::MelTables mel_tab{};
-  void* d_pcm = nullptr;              // staging for host PCM
+  void* d_pcm = nullptr;              // staging for host PCM (the buffer the next mel reads)
   size_t d_pcm_bytes = 0;
+  // double-buffered upload (wb_pcm_prefetch): the next batch's H2D runs on copy_stream under the
+  // current batch's encoder
+  void* d_pcm_buf[2] = {nullptr, nullptr};
+  int pcm_cur = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};   // recorded on copy_stream after the upload into buffer i
+  cudaEvent_t ev_mel_read[2] = {nullptr, nullptr};    // recorded on stream after the mel kernel that read buffer i
+  const void* pf_host[2] = {nullptr, nullptr};        // host pointer / size a prefetched buffer was filled from
+  size_t pf_bytes[2] = {0, 0};
   float* d_mel = nullptr;             // [clip][n_mel][n_len]
   size_t d_mel_floats = 0;
   int* d_clip_max = nullptr;

@@ -62,6 +62,7 @@ extern "C" {
     pub fn wb_pcm_to_mel(ctx: *mut wb_ctx, pcm: *const f32, n_samples: usize, n_clips: c_int) -> c_int;
     pub fn wb_pcm_to_mel_device(ctx: *mut wb_ctx, pcm_dev: *const f32, n_samples: usize, n_clips: c_int) -> c_int;
     pub fn wb_pcm16_to_mel(ctx: *mut wb_ctx, pcm: *const i16, n_samples: usize, n_clips: c_int) -> c_int;
+    pub fn wb_pcm_prefetch(ctx: *mut wb_ctx, pcm: *const c_void, n_bytes: usize) -> c_int;
     pub fn wb_mel_dims(ctx: *const wb_ctx, n_mel: *mut c_int, n_len: *mut c_int, n_clips: *mut c_int) -> c_int;
     pub fn wb_mel_read(ctx: *mut wb_ctx, clip: c_int, out: *mut f32, cap_floats: usize) -> c_int;
     pub fn wb_mel_write(ctx: *mut wb_ctx, mel: *const f32, n_mel: c_int, n_len: c_int, n_clips: c_int) -> c_int;
