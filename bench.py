@@ -191,6 +191,58 @@ def run_reference(args, pkg, rank: int):
     }), flush=True)
 
 
+def decoder_bytes_per_step(hp, B: int, p_avg: float) -> dict:
+    """Algorithmic HBM bytes of one single-token decode step for B sequences: the decoder
+    weights once (F16), plus per sequence the cross-attention K/V of every layer and the self-attention
+    K/V up to the current position."""
+    d, L, T = hp.n_text_state, hp.n_text_layer, hp.n_audio_ctx
+    w = (14 * L * d * d + hp.n_vocab * d) * 2
+    cross = L * 2 * T * d * 2
+    self_kv = L * 2 * p_avg * d * 2
+    return {"weights": float(w), "cross_kv_per_seq": float(cross), "self_kv_per_seq": float(self_kv),
+            "total": float(w + B * (cross + self_kv))}
+
+
+def decoder_leg(args, pkg, api, torch, dist, rank, world, local_rank, dev, barrier, peaks):
+    """BASELINE.json's second metric, decoder tokens/sec, on configs[2]: whisper small, batch 32, greedy
+    decode to 224 tokens (device-side loop, one CUDA graph replayed per position)."""
+    arch, B, n_new = args.dec_arch, args.dec_batch, args.dec_tokens
+    hp = pkg.ggml_file.ARCHS[arch]
+    model = ensure_model(pkg, arch, rank, barrier)
+    ctx = api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=args.samples, device=local_rank,
+                                 decode_capacity=True)
+    pcm = torch.from_numpy(pkg.synth.make_clips(B, first_seg=7000 + rank * B, n_samples=args.samples)).to(dev)
+    api.whisper_pcm_to_mel(ctx, pcm)
+    api.whisper_encode(ctx, 1, [0] * B, clip_ids=list(range(B)))
+    ctx.sync()
+    prompt = [ctx.token_sot]
+    times = []
+    toks = None
+    for it in range(1 + args.dec_reps):           # first call captures the step graph (warm-up)
+        barrier()
+        toks, _, lens = api.whisper_decode_greedy(ctx, prompt, n_new, n_seqs=B, eot=-1)   # eot -1: never stops early
+        times.append(ctx.timings()["t_decode_us"] * 1e-6)
+    t = float(np.min(times[1:]))
+    if world > 1:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    ctx.close()
+    by = decoder_bytes_per_step(hp, B, (len(prompt) + n_new) / 2.0)
+    gbs = by["total"] * n_new / t / 1e9
+    return {
+        "metric": "decoder tokens/sec (greedy)", "value": world * B * n_new / t, "unit": "tokens/s",
+        "config": {"workload": f"whisper {arch} greedy decode to {n_new} tokens, batch {B} per GPU, after mel + encode "
+                               f"of {B} x 30 s segments", "arch": arch, "batch_per_gpu": B, "new_tokens": n_new},
+        "ms_per_token_step": t / n_new * 1e3, "timing": "CUDA events around the whole greedy call on its stream "
+        "(prompt pass + one CUDA-graph replay per position), best of %d" % args.dec_reps,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                     "frac": gbs / float(peaks["hbm_gbs"]), "bytes_per_step": by},
+        "all_lengths_equal_new_tokens": bool((np.asarray(lens) == n_new).all()),
+        "first_tokens_seq0": [int(x) for x in toks[0][:8]],
+    }
+
+
 # ---------------------------------------------------------------------------------------------
 def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
     import torch
@@ -385,10 +437,15 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
             "cpu_baseline": cpu,
             "digest_segment0": float(digests[0]),
         }
-        print(json.dumps(out), flush=True)
     ctx.close()
     for cx in e2e_ctx:
         cx.close()
+    dec = None
+    if not args.no_decoder:
+        dec = decoder_leg(args, pkg, api, torch, dist, rank, world, local_rank, dev, barrier, measured_peaks())
+    if rank == 0:
+        out["decoder"] = dec
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -404,6 +461,11 @@ def main():
     ap.add_argument("--samples", type=int, default=480000)
     ap.add_argument("--cpu-segments", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the decoder tokens/sec leg")
+    ap.add_argument("--dec-arch", default="small")
+    ap.add_argument("--dec-batch", type=int, default=32)
+    ap.add_argument("--dec-tokens", type=int, default=224)
+    ap.add_argument("--dec-reps", type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

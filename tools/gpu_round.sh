@@ -12,7 +12,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 tail -2 gpurun_out/smoke.log
 TAG=${WB_TAG:-cur}
 timeout 600 python bench.py --steps 10 --warmup 3 ${WB_BENCH_FLAGS:---no-cpu-baseline} > gpurun_out/bench_base_$TAG.json 2> gpurun_out/bench_base_$TAG.err; echo "bench base exit $?" | tee -a gpurun_out/summary.txt
-timeout 600 python bench.py --arch medium --batch 16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_medium_$TAG.json 2> gpurun_out/bench_medium_$TAG.err; echo "bench medium exit $?" | tee -a gpurun_out/summary.txt
+timeout 600 python bench.py --arch medium --batch 16 --steps 5 --warmup 3 --no-cpu-baseline --no-decoder > gpurun_out/bench_medium_$TAG.json 2> gpurun_out/bench_medium_$TAG.err; echo "bench medium exit $?" | tee -a gpurun_out/summary.txt
 python - <<'PY'
 import json,glob,os
 for f in sorted(glob.glob("gpurun_out/bench_*_%s.json" % os.environ.get("WB_TAG","cur"))):
@@ -22,4 +22,13 @@ for f in sorted(glob.glob("gpurun_out/bench_*_%s.json" % os.environ.get("WB_TAG"
         print("  shares", {k: round(v,3) for k,v in d["kernels"]["shares_of_step"].items()})
     except Exception as e:
         print(f, "ERR", e)
+PY
+python - <<'PY'
+import json,os
+f="gpurun_out/bench_base_%s.json" % os.environ.get("WB_TAG","cur")
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1]).get("decoder")
+    if d: print("decoder: %.0f tokens/s, %.2f ms/step, %.0f GB/s (%.3f of HBM)" % (d["value"], d["ms_per_token_step"], d["roofline"]["achieved"], d["roofline"]["frac"]), d["all_lengths_equal_new_tokens"], d["first_tokens_seq0"])
+except Exception as e:
+    print("decoder ERR", e)
 PY

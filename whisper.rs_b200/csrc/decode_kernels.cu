@@ -27,6 +27,15 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
+// streaming 16-byte load (read-only path, do not keep the line in L1)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float block_max(float v, float* sh, int n_warps) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -320,6 +329,190 @@ argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ n
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Skinny linear layer of a decode step: out[r][n] = epi( sum_k x[r][k] * W[n][k] ) for R <= 32
+// activation rows (sequences) -- pure weight streaming, HBM-bound.  A 128-row tcgen05 tile would
+// leave 6 .. 24 CTAs on a 148-SM chip here (N = d .. 4d weight rows), so this kernel gives every
+// 16 weight rows their own CTA and uses warp-level mma.sync m16n8k16 (A = 16 weight rows, B = the
+// activations' 8-row groups): 4 warps split K, each lane streams its weight rows as 16-byte loads
+// straight from HBM (4 lanes cover 64 contiguous bytes of a row; the K order inside a 32-wide block
+// is permuted identically for A and B so that one 16-byte load feeds two MMAs), partial sums meet
+// in shared memory, and the epilogue (bias, column scale, GELU, f32 residual) writes out[r][n].
+// For the vocabulary projection it also emits each CTA's per-sequence top-2 (value, index), so the
+// arg-max never re-reads the logits (D5 + D6 fused).
+struct Top2;
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int DL_THREADS = 128;   // 4 warps: K split four ways
+constexpr int DL_ROWS = 16;       // weight rows (output features) per CTA
+
+__global__ void __launch_bounds__(DL_THREADS)
+decode_linear_kernel(const DecodeLinear a) {
+  __shared__ float red[4][DL_ROWS][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = lane & 3, g = lane >> 2;
+  const int n0 = blockIdx.x * DL_ROWS;
+  const int kw = a.K / 4;                       // this warp's K range (multiple of 16)
+  const int k_lo = warp * kw, k_hi = k_lo + kw;
+  // rows past N (ragged vocabulary) are clamped for the loads and masked at the store
+  const int ra = min(n0 + g, a.N - 1), rb = min(n0 + g + 8, a.N - 1);
+  const __half* wa = a.w + (size_t)ra * a.K + 8 * t;
+  const __half* wb = a.w + (size_t)rb * a.K + 8 * t;
+  const __half* xg = a.x + (size_t)g * a.ldx + 8 * t;   // activation row g of each 8-row group
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+  int k = k_lo;
+#pragma unroll 4
+  for (; k + 32 <= k_hi; k += 32) {
+    const uint4 A = ld_nc_v4(wa + k), B = ld_nc_v4(wb + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 X = *reinterpret_cast<const uint4*>(xg + (size_t)(8 * j) * a.ldx + k);
+      mma_16816(acc[j], A.x, B.x, A.y, B.y, X.x, X.y);
+      mma_16816(acc[j], A.z, B.z, A.w, B.w, X.z, X.w);
+    }
+  }
+  if (k < k_hi) {   // 16-wide tail (kw = 16 mod 32): lanes read 8 bytes
+    const uint2 A = *reinterpret_cast<const uint2*>(a.w + (size_t)ra * a.K + k + 4 * t);
+    const uint2 B = *reinterpret_cast<const uint2*>(a.w + (size_t)rb * a.K + k + 4 * t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint2 X = *reinterpret_cast<const uint2*>(a.x + (size_t)(8 * j + g) * a.ldx + k + 4 * t);
+      mma_16816(acc[j], A.x, B.x, A.y, B.y, X.x, X.y);
+    }
+  }
+  // C fragment: c0,c1 = (feature g, rows 2t, 2t+1 of group j), c2,c3 = (feature g+8, same rows)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[warp][g][8 * j + 2 * t] = acc[j][0];
+    red[warp][g][8 * j + 2 * t + 1] = acc[j][1];
+    red[warp][g + 8][8 * j + 2 * t] = acc[j][2];
+    red[warp][g + 8][8 * j + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  // ---- epilogue: thread -> (row r = tid / 4, features f = 4 (tid % 4) .. +3): a row's 16 features
+  // are written by 4 adjacent lanes as one contiguous run
+  const int r = tid >> 2, f0 = (tid & 3) * 4;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = f0 + i;
+    float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
+    const int n = n0 + f;
+    if (n < a.N) {
+      if (a.bias) x += a.bias[n];
+      if (a.colscale) x *= a.colscale[n];
+      x *= a.scale;
+      if (a.gelu) x = gelu_f16in(x);
+      if (a.residual && r < a.R) x += a.residual[(size_t)r * a.res_ld + n];
+    } else {
+      x = -INFINITY;
+    }
+    v[i] = x;
+  }
+  if (r < a.R) {
+    if (n0 + f0 + 3 < a.N && (a.out_ld & 3) == 0) {
+      if (a.out_f16) {
+        uint2 u;
+        u.x = pack_h2(v[0], v[1]);
+        u.y = pack_h2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + (size_t)r * a.out_ld + n0 + f0) = u;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)r * a.out_ld + n0 + f0) =
+            make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n0 + f0 + i < a.N) {
+          if (a.out_f16) reinterpret_cast<__half*>(a.out)[(size_t)r * a.out_ld + n0 + f0 + i] = __float2half_rn(v[i]);
+          else reinterpret_cast<float*>(a.out)[(size_t)r * a.out_ld + n0 + f0 + i] = v[i];
+        }
+    }
+  }
+  if (a.top2) {   // per-CTA top-2 of every sequence over this CTA's 16 vocabulary entries
+    float v1 = -INFINITY, v2 = -INFINITY;
+    int i1 = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (v[i] > v1) {
+        v2 = v1;
+        v1 = v[i];
+        i1 = n0 + f0 + i;
+      } else if (v[i] > v2) {
+        v2 = v[i];
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {   // merge the row's 4 lanes (lower index wins ties)
+      const float u1 = __shfl_xor_sync(0xffffffffu, v1, o), u2 = __shfl_xor_sync(0xffffffffu, v2, o);
+      const int j1 = __shfl_xor_sync(0xffffffffu, i1, o);
+      if (u1 > v1 || (u1 == v1 && j1 < i1)) {
+        v2 = fmaxf(v1, u2);
+        v1 = u1;
+        i1 = j1;
+      } else {
+        v2 = fmaxf(v2, u1);
+      }
+    }
+    if ((tid & 3) == 0 && r < a.R) {
+      float* dst = a.top2 + ((size_t)r * gridDim.x + blockIdx.x) * 3;
+      dst[0] = v1;
+      dst[1] = v2;
+      dst[2] = __int_as_float(i1);
+    }
+  }
+}
+
+// D6 from the per-CTA top-2 partials the vocabulary projection leaves ([seq][n_part][3])
+__global__ void __launch_bounds__(256)
+argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restrict__ next_tok,
+                       float* __restrict__ margin_out, int* __restrict__ out_tokens, float* __restrict__ out_margin,
+                       int* __restrict__ out_len, int* __restrict__ done, int max_new, const int* __restrict__ step_p,
+                       int eot) {
+  __shared__ Top2 sh[8];
+  const int s = blockIdx.x;
+  const float* p = part + (size_t)s * n_part * 3;
+  Top2 t{-INFINITY, -INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+    Top2 u{p[3 * i], p[3 * i + 1], __float_as_int(p[3 * i + 2])};
+    t = top2_merge(t, u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Top2 u;
+    u.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+    u.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+    u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    t = top2_merge(t, u);
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Top2 r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = top2_merge(r, sh[w]);
+    next_tok[s] = r.i1;
+    if (margin_out) margin_out[s] = r.v1 - r.v2;
+    if (out_tokens) {
+      const int step = *step_p;
+      if (!done[s] && step < max_new) {
+        out_tokens[(size_t)s * max_new + step] = r.i1;
+        if (out_margin) out_margin[(size_t)s * max_new + step] = r.v1 - r.v2;
+        out_len[s] = step + 1;
+        if (r.i1 == eot) done[s] = 1;
+      }
+    }
+  }
+}
+
 __global__ void advance_kernel(int* n_past, int add, int* step) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *n_past += add;
@@ -366,6 +559,21 @@ cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next
                           cudaStream_t st) {
   argmax_kernel<<<n_seq, 1024, 0, st>>>(logits, n_vocab, next_tok, margin, out_tokens, out_margin, out_len, done,
                                         max_new, step_dev, eot);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st) {
+  if (a.R < 1 || a.R > 32 || a.N < 1 || a.K % 64 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
+  decode_linear_kernel<<<(a.N + DL_ROWS - 1) / DL_ROWS, DL_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+int decode_linear_parts(int N) { return (N + DL_ROWS - 1) / DL_ROWS; }
+
+cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
+                                   int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
+                                   const int* step_dev, int eot, cudaStream_t st) {
+  argmax_partials_kernel<<<n_seq, 256, 0, st>>>(part, n_part, next_tok, margin, out_tokens, out_margin, out_len, done,
+                                                max_new, step_dev, eot);
   return cudaGetLastError();
 }
 

@@ -288,7 +288,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_
               if (n0 + j < args.N) v[j] += rp[j];
           }
         }
-        const long long o = (long long)b * e.out_bstride + (long long)m * e.out_ld + n0;
+        const long long o = e.out_slab_cols > 0
+                                ? (long long)(n0 / e.out_slab_cols) * e.out_slab_stride + (long long)m * e.out_ld +
+                                      (n0 % e.out_slab_cols)
+                                : (long long)b * e.out_bstride + (long long)m * e.out_ld + n0;
         if (e.out_f16) {
           __half* dst = reinterpret_cast<__half*>(e.out) + o;
           if (full_chunk) {

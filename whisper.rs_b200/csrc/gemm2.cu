@@ -52,6 +52,7 @@ struct Gemm2Args {
   int out_f16;
   int has_res;             // f32 residual tile fetched through res_map, added last
   int res_bcast;           // residual has no batch dimension (positional embedding)
+  int out_slab_cols;       // > 0: output column n lives in slab n / C at column n % C (out_map's third dimension)
   __half* vt_out;          // columns >= vt_col0 go to the transposed V buffer (see GemmEpilogue)
   int vt_col0, vt_heads, vt_head_rows, vt_ld, vt_T;
 };
@@ -391,7 +392,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&out_map, sbuf, n0, m_row0, it.b);
+          if (args.out_slab_cols > 0) tma_store_3d(&out_map, sbuf, n0 % args.out_slab_cols, m_row0, n0 / args.out_slab_cols);
+          else tma_store_3d(&out_map, sbuf, n0, m_row0, it.b);
           bulk_commit_group();
           if (args.has_res) {
             // prefetch the next chunk's residual into the other buffer once the store that last
@@ -475,6 +477,7 @@ cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
   a.out_f16 = g.epi.out_f16;
   a.has_res = g.res_map != nullptr;
   a.res_bcast = g.res_bcast;
+  a.out_slab_cols = g.epi.out_slab_cols;
   a.vt_out = g.epi.vt_out;
   a.vt_col0 = g.epi.vt_col0;
   a.vt_heads = g.epi.vt_heads;

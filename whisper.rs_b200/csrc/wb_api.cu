@@ -405,6 +405,7 @@ int alloc_activations(wb_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->hidden, S * T * 4 * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->enc_out, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->enc_f16, S * T * d))) return rc;
+  ctx->cross_slab = S * T * d;
   if ((rc = dev_alloc(ctx, &ctx->cross, S * T * Lt * 2 * d))) return rc;
   ctx->n_chk_slots = 4 + hp.n_audio_layer + 2 * hp.n_text_layer;
   if ((rc = dev_alloc(ctx, &ctx->d_chk, (size_t)ctx->n_chk_slots * S))) return rc;
@@ -807,7 +808,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
        tmap_out(&o_x, ctx->x, true, d, M, 1, d, 0, &terr) &&
        tmap_out(&o_qk, ctx->qk, false, 2 * d, M, 1, 2 * d, 0, &terr) &&
        tmap_out(&o_hid, ctx->hidden, false, 4 * d, M, 1, 4 * d, 0, &terr) &&
-       (Lt == 0 || tmap_out(&o_cross, ctx->cross, false, (uint64_t)Lt * 2 * d, M, 1, (uint64_t)Lt * 2 * d, 0, &terr));
+       (Lt == 0 || tmap_out(&o_cross, ctx->cross, false, d, M, (uint64_t)2 * Lt, d, ctx->cross_slab, &terr));
   if (!ok) return fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
   ap.B = n_seg;
   ap.T = T;
@@ -921,13 +922,14 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     GemmEpilogue e;
     e.out = ctx->cross;
     e.out_f16 = 1;
-    e.out_ld = Lt * 2 * d;
+    e.out_ld = d;
+    e.out_slab_cols = d;                       // column block j of the fused weight -> slab j ([rows][d])
+    e.out_slab_stride = (long long)ctx->cross_slab;
     if ((rc = run_gemm(ctx, m_enc, M, 1, ctx->cross_kv, e, "gemm_cross", &o_cross))) return rc;
     if (chk) {
-      const long long ld = (long long)Lt * 2 * d;
       for (int il = 0; il < Lt; ++il) {
-        if ((rc = probe_f16(4 + L + 2 * il, ctx->cross + (size_t)il * 2 * d, T, d, ld, (long long)T * ld))) return rc;
-        if ((rc = probe_f16(5 + L + 2 * il, ctx->cross + (size_t)il * 2 * d + d, T, d, ld, (long long)T * ld))) return rc;
+        if ((rc = probe_f16(4 + L + 2 * il, ctx->cross + (size_t)(2 * il) * ctx->cross_slab, T, d, d, (long long)T * d))) return rc;
+        if ((rc = probe_f16(5 + L + 2 * il, ctx->cross + (size_t)(2 * il + 1) * ctx->cross_slab, T, d, d, (long long)T * d))) return rc;
       }
     }
   }
@@ -950,12 +952,12 @@ int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out) {
 int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v) {
   if (!ctx || seg < 0 || seg >= ctx->enc_n_seg || layer < 0 || layer >= ctx->hp.n_text_layer) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const int T = ctx->hp.n_audio_ctx, d = ctx->hp.n_audio_state, Lt = ctx->hp.n_text_layer;
-  const size_t ld = (size_t)Lt * 2 * d;
-  const __half* base = ctx->cross + (size_t)seg * T * ld + (size_t)layer * 2 * d;
-  // strided device rows -> the reference's dense [n_ctx][d] slice of memory_cross_k/v (2018-2030)
-  if (k) WB_CK(cudaMemcpy2DAsync(k, (size_t)d * 2, base, ld * 2, (size_t)d * 2, T, cudaMemcpyDeviceToHost, ctx->stream));
-  if (v) WB_CK(cudaMemcpy2DAsync(v, (size_t)d * 2, base + d, ld * 2, (size_t)d * 2, T, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n = (size_t)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  // the reference's dense [n_ctx][d] slice of memory_cross_k/v (2018-2030)
+  const __half* kb = ctx->cross + (size_t)(2 * layer) * ctx->cross_slab + (size_t)seg * n;
+  const __half* vb = ctx->cross + (size_t)(2 * layer + 1) * ctx->cross_slab + (size_t)seg * n;
+  if (k) WB_CK(cudaMemcpyAsync(k, kb, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) WB_CK(cudaMemcpyAsync(v, vb, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
   return WB_OK;
 }

@@ -98,7 +98,9 @@ struct wb_ctx {
   __half* hidden = nullptr;           // [seg*T][4d]
   float* enc_out = nullptr;           // [seg*T][d] f32 (ln_post)
   __half* enc_f16 = nullptr;
-  __half* cross = nullptr;            // [seg*T][Lt*2*d]  (memory_cross_k/v)
+  __half* cross = nullptr;            // memory_cross_k/v: [2*Lt slabs][max_segments*T][d]; K of text layer il is slab
+                                      // 2*il, V is slab 2*il+1 (each a dense [seg][T][d] matrix, as in src/main.rs:2018-2030)
+  size_t cross_slab = 0;              // elements per slab = max_segments * T * d
   int Tp = 0;
   int enc_n_seg = 0;                  // segments of the last wb_encode
   double* d_chk = nullptr;            // [slot][max_segments]
@@ -112,6 +114,8 @@ struct wb_ctx {
   __half *d_ln = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_hid = nullptr, *d_q = nullptr, *d_lnf = nullptr;
   wb::ActMaps m_ln, m_att, m_hid, m_lnf;         // swap-AB activation operands
   float* d_logits = nullptr;                     // [seq][n_vocab] of the last position  (logits, 351)
+  float* d_top2 = nullptr;            // [32][ceil(n_vocab/16)][3] per-CTA top-2 of the vocabulary projection
+  bool logits_top2_valid = false;
   int *d_tokens = nullptr, *d_next = nullptr, *d_out_tokens = nullptr, *d_done = nullptr, *d_out_len = nullptr;
   int *d_npast = nullptr, *d_step = nullptr;
   float *d_margin = nullptr, *d_out_margin = nullptr;

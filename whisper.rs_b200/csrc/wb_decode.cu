@@ -32,6 +32,11 @@ static int make_act_maps(wb_ctx* ctx, ActMaps& am, const __half* base, int K, in
 }
 
 // C^T = W * X^T : out[r][n_out] for r < R
+// few rows (one token per sequence, <= 32 sequences): the HBM-bound skinny kernel, every 16 weight
+// rows on their own CTA (decode_kernels.cu); more rows: the tcgen05 GEMM in swap-AB form
+static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const ActMaps& act, int R, GemmEpilogue epi,
+                           const char* family, float* top2 = nullptr);
+
 static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, int R, GemmEpilogue epi,
                             const char* family) {
   GemmProblem g;
@@ -49,6 +54,31 @@ static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, in
   g.epi = epi;
   LaunchTimer t(ctx, family);
   WB_CK(launch_gemm(g, ctx->num_sms, ctx->stream));
+  return WB_OK;
+}
+
+static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const ActMaps& act, int R, GemmEpilogue epi,
+                           const char* family, float* top2) {
+  if (R > 32 || l.K % 64 != 0) return run_gemm_swapped(ctx, l, act, R, epi, family);
+  DecodeLinear a;
+  a.w = l.w;
+  a.x = x;
+  a.N = l.N;
+  a.K = l.K;
+  a.R = R;
+  a.ldx = l.K;
+  a.bias = epi.bias ? epi.bias : l.bias;
+  a.colscale = epi.colscale ? epi.colscale : l.colscale;
+  a.scale = epi.scale;
+  a.gelu = epi.gelu;
+  a.residual = epi.residual;
+  a.res_ld = epi.res_ld;
+  a.out = epi.out;
+  a.out_f16 = epi.out_f16;
+  a.out_ld = epi.out_ld;
+  a.top2 = top2;
+  LaunchTimer t(ctx, family);
+  WB_CK(launch_decode_linear(a, ctx->stream));
   return WB_OK;
 }
 
@@ -103,6 +133,7 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
   const size_t Sf = S < 256 ? 256 : S;
   if ((rc = dev_alloc(ctx, &ctx->d_lnf, Sf * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_logits, (size_t)S * hp.n_vocab))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_top2, (size_t)32 * decode_linear_parts(hp.n_vocab) * 3))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_tokens, R))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_next, (size_t)S))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_out_tokens, (size_t)S * n_ctx))) return rc;
@@ -130,7 +161,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
   const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, T = hp.n_audio_ctx;
   const int n_ctx = hp.n_text_ctx;
   const int R = n_seq * n_tok;
-  const long long ld_kv = (long long)Lt * 2 * d;
+  const long long ld_kv = d;   // cross K / V of one layer: dense [seg][T][d]
   cudaStream_t st = ctx->stream;
   int rc;
   {
@@ -149,7 +180,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->d_qkv;
       e.out_f16 = 1;
       e.out_ld = 3 * d;
-      if ((rc = run_gemm_swapped(ctx, l.qkv, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.qkv, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
       LaunchTimer t(ctx, "dec_self_attn");
@@ -164,7 +195,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
-      if ((rc = run_gemm_swapped(ctx, l.out, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.out, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
     {   // D3: cross-attention over memory_cross_k/v written by wb_encode
       LaunchTimer t(ctx, "dec_layernorm");
@@ -175,12 +206,12 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->d_q;
       e.out_f16 = 1;
       e.out_ld = d;
-      if ((rc = run_gemm_swapped(ctx, l.cq, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.cq, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
       LaunchTimer t(ctx, "dec_cross_attn");
-      const __half* kx = ctx->cross + (size_t)il * 2 * d;
-      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + d, ld_kv, n_seq, n_tok, T, H, ctx->d_att, ctx->d_part_o,
+      const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab;
+      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + ctx->cross_slab, ld_kv, n_seq, n_tok, T, H, ctx->d_att, ctx->d_part_o,
                                      ctx->d_part_ml, n_split, st));
     }
     {
@@ -190,7 +221,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
-      if ((rc = run_gemm_swapped(ctx, l.cout, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.cout, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
     {   // D4: MLP
       LaunchTimer t(ctx, "dec_layernorm");
@@ -202,7 +233,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->d_hid;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
-      if ((rc = run_gemm_swapped(ctx, l.fc1, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.fc1, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
       GemmEpilogue e;
@@ -211,7 +242,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
-      if ((rc = run_gemm_swapped(ctx, l.fc2, ctx->m_hid, R, e, "dec_gemm"))) return rc;
+      if ((rc = run_linear_rows(ctx, l.fc2, ctx->d_hid, ctx->m_hid, R, e, "dec_gemm"))) return rc;
     }
   }
   {   // D5: logits of the last position of every sequence
@@ -224,9 +255,24 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
     e.out = ctx->d_logits;
     e.out_f16 = 0;
     e.out_ld = hp.n_vocab;
-    if ((rc = run_gemm_swapped(ctx, ctx->logits_lin, ctx->m_lnf, n_seq, e, "dec_gemm_logits"))) return rc;
+    // <= 32 sequences: the skinny kernel also leaves per-CTA top-2 partials, so D6 never re-reads the logits
+    ctx->logits_top2_valid = n_seq <= 32 && ctx->logits_lin.K % 64 == 0;
+    if ((rc = run_linear_rows(ctx, ctx->logits_lin, ctx->d_lnf, ctx->m_lnf, n_seq, e, "dec_gemm_logits",
+                              ctx->logits_top2_valid ? ctx->d_top2 : nullptr)))
+      return rc;
   }
   return WB_OK;
+}
+
+// D6 bookkeeping after a decode pass: from the top-2 partials when the skinny logits kernel ran
+static cudaError_t run_argmax(wb_ctx* ctx, int n_seqs, int max_new, int eot) {
+  const ModelHParams& hp = ctx->hp;
+  if (ctx->logits_top2_valid)
+    return launch_argmax_partials(ctx->d_top2, decode_linear_parts(hp.n_vocab), n_seqs, ctx->d_next, ctx->d_margin,
+                                  ctx->d_out_tokens, ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step,
+                                  eot, ctx->stream);
+  return launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens, ctx->d_out_margin,
+                       ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, ctx->stream);
 }
 
 static int check_decode_args(wb_ctx* ctx, int n_tok, int n_past, int n_seq) {
@@ -307,8 +353,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   if ((rc = decode_pass(ctx, ctx->d_tokens, n_seqs, n_prompt))) return rc;
   {
     LaunchTimer t(ctx, "dec_argmax");
-    WB_CK(launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
-                        ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st));
+    WB_CK(run_argmax(ctx, n_seqs, max_new, eot));
     WB_CK(launch_advance(ctx->d_npast, n_prompt, ctx->d_step, st));
   }
   WB_CK(cudaStreamSynchronize(st));   // `toks` is a stack temporary
@@ -327,8 +372,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
     if (rc == WB_OK) {
-      e1 = launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
-                         ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st);
+      e1 = run_argmax(ctx, n_seqs, max_new, eot);
       e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
     }
     cudaError_t e3 = cudaStreamEndCapture(st, &graph);
@@ -352,8 +396,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");
-      WB_CK(launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens,
-                          ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, st));
+      WB_CK(run_argmax(ctx, n_seqs, max_new, eot));
       WB_CK(launch_advance(ctx->d_npast, 1, ctx->d_step, st));
     }
     n_past += 1;

@@ -32,6 +32,11 @@ struct GemmEpilogue {
   int out_f16 = 1;
   long long out_bstride = 0;
   int out_ld = 0;
+  // column slabs: with out_slab_cols = C > 0, column n goes to slab n / C at column n % C:
+  //   out[(n / C) * out_slab_stride + m*out_ld + n % C]   (batch must be 1)
+  // -- the cross-attention K/V of every text layer leave one GEMM as per-layer [rows][d] matrices
+  int out_slab_cols = 0;
+  long long out_slab_stride = 0;
   // columns n >= vt_col0 are written transposed (time contiguous) as F16: with nn = n - vt_col0,
   //   vt_out[((seg*vt_heads + nn/64) * vt_head_rows + nn%64) * vt_ld + t],  seg = m / vt_T, t = m % vt_T
   // which is the reference's V layout `[T, Dh, H]` per segment (1914-1920); each head block holds
@@ -128,6 +133,26 @@ cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, co
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
                           float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
                           cudaStream_t st);
+// skinny linear layer of a decode step (R <= 32 activation rows): out[r][n] = epi(sum_k x[r][k] W[n][k])
+struct DecodeLinear {
+  const __half* w = nullptr;       // [N][K] f16, K contiguous
+  const __half* x = nullptr;       // [32][ldx] f16 (rows >= R may hold anything finite; they are never stored)
+  int N = 0, K = 0, R = 0, ldx = 0;
+  const float* bias = nullptr;     // [N]
+  const float* colscale = nullptr; // [N]
+  float scale = 1.0f;
+  int gelu = 0;
+  const float* residual = nullptr; // f32 [R][res_ld], added last
+  int res_ld = 0;
+  void* out = nullptr;             // [R][out_ld]
+  int out_f16 = 1, out_ld = 0;
+  float* top2 = nullptr;           // optional [R][n_parts][3]: per-CTA (top value, second value, index bits)
+};
+cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st);
+int decode_linear_parts(int N);    // CTAs (= top-2 partials per sequence) for N output features
+cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
+                                   int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
+                                   const int* step_dev, int eot, cudaStream_t st);
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st);
 
 }  // namespace wb
