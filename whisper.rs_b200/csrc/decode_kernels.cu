@@ -30,7 +30,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // streaming 16-byte load (read-only path, do not keep the line in L1)
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
@@ -183,19 +183,28 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
     const int row = s * n_tok + i;
     float qf[8];
     unpack8(*reinterpret_cast<const uint4*>(q + (size_t)row * d + h * DH + ch * 8), qf);
-    for (int t0 = warp * 4; t0 < n; t0 += (CROSS_THREADS / 32) * 4) {
-      const int t = t0 + sub;
-      float acc = 0.0f;
-      if (t < n) {
+    // 4 independent 16-byte loads in flight per lane (the stream is pure HBM latency otherwise)
+    constexpr int RPI = (CROSS_THREADS / 32) * 4;   // rows per CTA iteration
+    for (int t0 = warp * 4; t0 < n; t0 += 4 * RPI) {
+      uint4 kv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * RPI + sub;
+        kv[u] = t < n ? ld_nc_v4(kb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * RPI + sub;
         float kf[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(kb + (size_t)t * ld)), kf);
+        unpack8(kv[u], kf);
+        float acc = 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc = fmaf(qf[j], kf[j], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (ch == 0 && t < n) sc[t] = acc;
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (ch == 0 && t < n) sc[t] = acc;
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -212,14 +221,23 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < n; t0 += (CROSS_THREADS / 32) * 4) {
-      const int t = t0 + sub;
-      if (t < n) {
-        const float p = __half2float(__float2half_rn(sc[t] * inv));   // P -> F16 before P.V
-        float vf[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(vb + (size_t)t * ld)), vf);
+    for (int t0 = warp * 4; t0 < n; t0 += 4 * RPI) {
+      uint4 vv[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * RPI + sub;
+        vv[u] = t < n ? ld_nc_v4(vb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * RPI + sub;
+        if (t < n) {
+          const float p = __half2float(__float2half_rn(sc[t] * inv));   // P -> F16 before P.V
+          float vf[8];
+          unpack8(vv[u], vf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
+        }
       }
     }
 #pragma unroll
@@ -343,7 +361,8 @@ argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ n
 struct Top2;
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                           uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  // (not volatile: a pure function of its operands, so loads of later k-blocks may be hoisted above it)
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -370,7 +389,28 @@ decode_linear_kernel(const DecodeLinear a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
   int k = k_lo;
-#pragma unroll 4
+  // 4 k-blocks of fragments (24 x 16-byte loads per lane) are requested before the first MMA uses
+  // them: the kernel is pure HBM / L2 latency otherwise
+  constexpr int U = 4;
+  for (; k + 32 * U <= k_hi; k += 32 * U) {
+    uint4 A[U], B[U], X[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      A[u] = ld_nc_v4(wa + k + 32 * u);
+      B[u] = ld_nc_v4(wb + k + 32 * u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) X[u][j] = *reinterpret_cast<const uint4*>(xg + (size_t)(8 * j) * a.ldx + k + 32 * u);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mma_16816(acc[j], A[u].x, B[u].x, A[u].y, B[u].y, X[u][j].x, X[u][j].y);
+        mma_16816(acc[j], A[u].z, B[u].z, A[u].w, B[u].w, X[u][j].z, X[u][j].w);
+      }
+  }
   for (; k + 32 <= k_hi; k += 32) {
     const uint4 A = ld_nc_v4(wa + k), B = ld_nc_v4(wb + k);
 #pragma unroll
