@@ -346,11 +346,10 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
     l0 = ctx.timings()["n_kernel_launches"]
     ms_dev = timed(step_device, K)
     launches = ctx.timings()["n_kernel_launches"] - l0
-    digests = ctx.encoder_digest(B)
-    if world > 1:   # the one collective: final gather of the per-segment digests
-        g = [torch.zeros(B, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(g, torch.from_numpy(digests).to(dev))
-        digests = torch.cat(g).cpu().numpy()
+    # the one collective of the path: final gather of the small per-segment results (contiguous blocks of
+    # B segments per rank, NCCL all_gather)
+    digests = pkg.shard.gather_segment_results(ctx.encoder_digest(B), pkg.shard.segments_for_rank(world * B, rank, world, True),
+                                               world * B, device=dev if world > 1 else None)
     # ---- timed region 2: end to end through the host-facing call
     run_e2e(4)   # warm-up (both contexts)
     ms_e2e = run_e2e(K)

@@ -7,7 +7,8 @@ The directory name carries a dot, so it is loaded through `__graft_entry__.load_
 
   ggml_file  -- ggml-v1 model files: writer (random-init fixtures) + host reader
   synth      -- seeded synthetic 16 kHz PCM
+  shard      -- segment -> GPU assignment and the final gather (the path's only collective)
   cabi       -- ctypes binding of csrc/libwhisper_b200.so (the C-ABI drop-in boundary)
   api        -- host-side mirror of the reference's functions over the C-ABI
 """
-from . import ggml_file, synth  # noqa: F401
+from . import ggml_file, shard, synth  # noqa: F401

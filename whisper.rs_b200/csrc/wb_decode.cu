@@ -392,7 +392,8 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     if (n_past + 1 > n_ctx) break;   // text context full
     if (use_graph) {
       WB_CK(cudaGraphLaunch(ctx->step_graph, st));
-      ctx->tm.n_kernel_launches += 9 * hp.n_text_layer + 5;
+      // per layer: 3 LayerNorm + 6 linear + self-attn + cross-attn; + embed, final LN, logits, arg-max, advance
+      ctx->tm.n_kernel_launches += 11 * hp.n_text_layer + 5;
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");
