@@ -25,6 +25,7 @@ constexpr int F = 16;                        // frames per CTA
 constexpr int NFFT = 400, HOP = 160, NBIN = 201;
 constexpr int SPAN = HOP * (F - 1) + NFFT;   // 2800 samples
 constexpr int MEL_THREADS = 256;
+constexpr int MEL_MAX_NZ = 1024, MEL_MAX_MEL = 128;
 
 struct MelSmem {
   float pcm[SPAN];
@@ -34,6 +35,9 @@ struct MelSmem {
   float2 w200[200];
   float2 w400[NBIN];
   float hann[NFFT];
+  float fw[MEL_MAX_NZ];     // non-zero filterbank taps, mel after mel (each bin feeds at most two slaney filters)
+  int2 frange[MEL_MAX_MEL]; // per mel: first bin, first tap index in fw (taps = bins frange[j].x .. of the next start)
+  int fcount[MEL_MAX_MEL];
 };
 
 __device__ __forceinline__ float2 cmul(float2 x, float2 y) {
@@ -65,6 +69,12 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
   for (int i = tid; i < 200; i += MEL_THREADS) s.w200[i] = tb.tw200[i];
   for (int i = tid; i < NBIN; i += MEL_THREADS) s.w400[i] = tb.tw400[i];
   for (int i = tid; i < NFFT; i += MEL_THREADS) s.hann[i] = tb.hann[i];
+  for (int i = tid; i < tb.n_nz; i += MEL_THREADS) s.fw[i] = tb.filt_nz[i];
+  for (int i = tid; i < tb.n_mel; i += MEL_THREADS) {
+    const int2 rg = tb.filt_range[i];
+    s.frange[i] = make_int2(rg.x, tb.filt_start[i]);
+    s.fcount[i] = rg.y - rg.x;
+  }
   if (I16) {
     const int16_t* pcm = reinterpret_cast<const int16_t*>(pcm_v) + (size_t)clip * n_samples;
     // convert_integer_to_float_audio (1673-1679): s / 32768.0 (exact in f32)
@@ -106,7 +116,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
                    csub(e0, o0), csub(e1, o1), csub(e2, o2), csub(e3, o3)};
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) {
-      const float2 w = s.w200[(n2 * k1) % 200];
+      const float2 w = s.w200[n2 * k1];   // n2 k1 <= 24 * 7 < 200
       s.a[f][k1 * 25 + n2] = (k1 == 0) ? y[0] : cmul(y[k1], w);
     }
   }
@@ -124,7 +134,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
       float2 acc = x[0];
 #pragma unroll
       for (int a = 1; a < 5; ++a) acc = cadd(acc, cmul(x[a], s.w200[40 * ((a * c) % 5)]));
-      if (c != 0 && bb != 0) acc = cmul(acc, s.w200[(8 * bb * c) % 200]);
+      if (c != 0 && bb != 0) acc = cmul(acc, s.w200[8 * bb * c]);   // W25^(b c) = W200^(8 b c), 8 b c <= 128
       s.b[f][k1 * 25 + bb * 5 + c] = acc;
     }
   }
@@ -166,10 +176,13 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
     const int j = it / F, f = it - j * F;
     const int i = i0 + f;
     if (i >= n_len) continue;
-    const int2 rg = __ldg(&tb.filt_range[j]);
-    const float* fr = tb.filt + (size_t)j * NBIN;
+    // taps in bin order, as the reference's sequential f32 sum (exact zeros contribute nothing)
+    const int2 rg = s.frange[j];
+    const float* pw = &s.pw[f][rg.x];
+    const float* fw = &s.fw[rg.y];
+    const int nt = s.fcount[j];
     float sum = 0.0f;
-    for (int k = rg.x; k < rg.y; ++k) sum = fmaf(s.pw[f][k], __ldg(fr + k), sum);
+    for (int k = 0; k < nt; ++k) sum = fmaf(pw[k], fw[k], sum);
     sum = fmaxf(sum, 1e-10f);
     const float v = log10f(sum);
     out[(size_t)j * n_len + i] = v;

@@ -42,54 +42,65 @@ __global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int 
 // F16 store = the rounding the following matmul applies to its activation operand.
 constexpr int LN_MAX_V4 = 10;   // d <= 1280
 
+// NV4 = float4 per lane (ceil(d / 128)), RPW = rows per warp (all of a warp's rows are requested
+// before the first is reduced).
+template <int NV4, int RPW>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long in_row_stride, const float* __restrict__ w,
                  const float* __restrict__ b, int rows, int d, __half* __restrict__ out_f16,
                  float* __restrict__ out_f32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row0 = warp * RPW;
+  if (row0 >= rows) return;
   const int nv4 = d >> 2;   // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * in_row_stride);
-  float4 v[LN_MAX_V4];
-  float sum = 0.0f;
+  float4 v[RPW][NV4];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv4) {
-      v[i] = xr[idx];
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int r = 0; r < RPW; ++r) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)min(row0 + r, rows - 1) * in_row_stride);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) v[r][i] = xr[idx];
     }
   }
-  const float mean = warp_sum(sum) / (float)d;
-  float sq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv4) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)d + 1e-5f);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv4) {
-      const float4 ww = __ldg(w4 + idx), bb = __ldg(b4 + idx);
-      float4 y;
-      y.x = ww.x * (v[i].x * rstd) + bb.x;
-      y.y = ww.y * (v[i].y * rstd) + bb.y;
-      y.z = ww.z * (v[i].z * rstd) + bb.z;
-      y.w = ww.w * (v[i].w * rstd) + bb.w;
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)warp * d)[idx] = y;
-      if (out_f16) {
-        uint2 u;
-        u.x = pack_h2(y.x, y.y);
-        u.y = pack_h2(y.z, y.w);
-        reinterpret_cast<uint2*>(out_f16 + (size_t)warp * d)[idx] = u;
+  for (int r = 0; r < RPW; ++r) {
+    if (row0 + r >= rows) break;
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+      if (lane + 32 * i < nv4) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+      if (lane + 32 * i < nv4) {
+        float4& t = v[r][i];
+        t.x -= mean; t.y -= mean; t.z -= mean; t.w -= mean;
+        sq += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)d + 1e-5f);
+    const size_t orow = (size_t)(row0 + r) * d;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) {
+        const float4 ww = __ldg(w4 + idx), bb = __ldg(b4 + idx);
+        float4 y;
+        y.x = ww.x * (v[r][i].x * rstd) + bb.x;
+        y.y = ww.y * (v[r][i].y * rstd) + bb.y;
+        y.z = ww.z * (v[r][i].z * rstd) + bb.z;
+        y.w = ww.w * (v[r][i].w * rstd) + bb.w;
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + orow)[idx] = y;
+        if (out_f16) {
+          uint2 u;
+          u.x = pack_h2(y.x, y.y);
+          u.y = pack_h2(y.z, y.w);
+          reinterpret_cast<uint2*>(out_f16 + orow)[idx] = u;
+        }
       }
     }
   }
@@ -147,9 +158,17 @@ cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int
                              float* out_f32, cudaStream_t st, long long in_row_stride) {
   if (d % 4 != 0 || d > 128 * LN_MAX_V4) return cudaErrorInvalidValue;
   if (in_row_stride <= 0) in_row_stride = d;
-  const int warps_per_block = 8;
-  layernorm_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(
-      x, in_row_stride, w, b, rows, d, out_f16, out_f32);
+  const int nv = (d / 4 + 31) / 32;   // float4 per lane
+  auto go = [&](auto kernel, int rpw) {
+    const int warps = (rows + rpw - 1) / rpw;
+    kernel<<<(warps + 7) / 8, 256, 0, st>>>(x, in_row_stride, w, b, rows, d, out_f16, out_f32);
+  };
+  // one row per warp: measured on B200 (base, 24000 rows of 512), 2 and 4 rows per warp in flight were
+  // slower (250 vs 224 us per step over 13 launches) -- the rows mostly come out of L2, where the previous
+  // GEMM left them
+  if (nv <= 4) go(layernorm_kernel<4, 1>, 1);
+  else if (nv <= 8) go(layernorm_kernel<8, 1>, 1);
+  else go(layernorm_kernel<LN_MAX_V4, 1>, 1);
   return cudaGetLastError();
 }
 

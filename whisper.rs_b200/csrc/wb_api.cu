@@ -382,7 +382,22 @@ int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
   WB_CK(cudaMemcpy(d_w400, w400.data(), 1608, cudaMemcpyHostToDevice));
   WB_CK(cudaMemcpy(d_filt, filt.data(), filt.size() * 4, cudaMemcpyHostToDevice));
   WB_CK(cudaMemcpy(d_range, range.data(), (size_t)n_mel * 8, cudaMemcpyHostToDevice));
-  ctx->mel_tab = MelTables{d_hann, d_w200, d_w400, d_filt, d_range, n_mel};
+  // compact taps: [lo, hi) of each mel back to back (zeros inside the span are kept: the sum order stays bin order)
+  std::vector<float> nz;
+  std::vector<int> start(n_mel);
+  for (int j = 0; j < n_mel; ++j) {
+    start[j] = (int)nz.size();
+    for (int k = range[j].x; k < range[j].y; ++k) nz.push_back(filt[(size_t)j * 201 + k]);
+  }
+  if (nz.size() > 1024 || n_mel > 128)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: mel filterbank too dense for the front-end kernel");
+  float* d_nz;
+  int* d_start;
+  if ((rc = dev_alloc(ctx, &d_nz, nz.size() ? nz.size() : 1, false))) return rc;
+  if ((rc = dev_alloc(ctx, &d_start, (size_t)n_mel, false))) return rc;
+  WB_CK(cudaMemcpy(d_nz, nz.data(), nz.size() * 4, cudaMemcpyHostToDevice));
+  WB_CK(cudaMemcpy(d_start, start.data(), (size_t)n_mel * 4, cudaMemcpyHostToDevice));
+  ctx->mel_tab = MelTables{d_hann, d_w200, d_w400, d_filt, d_range, n_mel, d_nz, d_start, (int)nz.size()};
   return WB_OK;
 }
 

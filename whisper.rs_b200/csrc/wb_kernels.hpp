@@ -94,6 +94,9 @@ struct MelTables {            // device pointers, built once per context
   const float* filt;          // [n_mel][201]
   const int2* filt_range;     // per mel: [lo, hi) of nonzero taps
   int n_mel;
+  const float* filt_nz;       // the taps of [lo, hi) of every mel, concatenated
+  const int* filt_start;      // per mel: offset of its first tap in filt_nz
+  int n_nz;
 };
 // frames -> log10 mel power, [clip][n_mel][n_len]; also per-clip running max (ordered-int encoding)
 cudaError_t launch_mel_frames(const MelTables& t, const void* pcm, int pcm_is_i16, size_t n_samples,
