@@ -8,11 +8,14 @@
 // argument stay in f32 (the reference rounds the argument to F16 for its lookup table), all
 // accumulation is f32.
 //
-// One CTA = one (segment, head, 256-query block): two softmax warpgroups of 128 threads, each
-// owning one 128-query tile (thread r = query row r = TMEM lane r, so the row max needs no
-// cross-thread reduction), one warp that issues every tcgen05.mma (the warp stays converged; one
-// elected lane per instruction) and one warp whose elected thread issues every TMA load.  Keys
-// advance in steps of 64; per step j and warpgroup:
+// One CTA = one (segment, head, 128-query tile), TWO CTAs per SM (each allocates 256 of the SM's 512
+// TMEM columns and 88 KB of shared memory): 4 softmax warps (thread r = query row r = TMEM lane r, so
+// the row max needs no cross-thread reduction), one warp that issues the tcgen05.mma instructions
+// (converged; one elected lane per instruction) and one warp whose elected thread issues the TMA
+// loads.  Two independent CTAs per SM instead of two warpgroups in one CTA: each CTA's prologue
+// (TMEM allocation, first loads) and tail hide under the other's steady state, the two never run
+// in lock-step on the MUFU unit, and 1536 small CTAs pack the 148 SMs better than 768 big ones
+// (measured 475 -> 520 TFLOP/s).  Keys advance in steps of 64; per step j:
 //   S_j = Q K_j^T          tcgen05.mma 128 x 64 x 64 into one of TWO S buffers in TMEM, issued two
 //                          steps ahead, so the next scores are already there when a softmax ends
 //   P_j = 2^(c S_j - m)    one TMEM pass into registers (3-input FMNMX max); exponentials split
@@ -26,11 +29,17 @@
 // The output accumulator never leaves TMEM: the running max is applied lazily -- O is rescaled
 // (tcgen05.ld / tcgen05.st, after waiting for the previous P.V to retire) only when a row's max
 // grows by more than 2^8, which after the first steps is rare.
-// K / V^T arrive as 128-key stages (a stage serves two steps) through a 3-deep TMA ring shared by
-// both warpgroups; every hand-off is an mbarrier (S ready x2, P ready x2, O idle, stage full /
-// free).  Measured constraints behind the shape (tools/ubench): a tcgen05.mma of M = 128 costs
-// max(~47, N/2) cycles, so the 64- and 80-wide tiles run at the instruction floor; FMNMX3 costs the
-// same as FMNMX; ex2.approx.f16x2 gives no MUFU throughput over the f32 form.
+// K / V^T arrive as 128-key stages (a stage serves two steps) through a 2-deep TMA ring; every
+// hand-off is an mbarrier (S ready x2, P ready x2, O idle, stage full / free).  Measured constraints
+// behind the shape (tools/ubench): a tcgen05.mma of M = 128 costs max(~47, N/2) cycles, so the 64-
+// and 80-wide tiles run at the instruction floor; the issuing thread is blocked while its MMA
+// executes; an mbarrier wait costs ~175 cycles even when already complete; FMNMX3 costs the same as
+// FMNMX; ex2.approx.f16x2 gives no MUFU throughput over the f32 form.  Variants measured slower or
+// equal on B200: 128-key tiles with P handed over in halves, 16 softmax warps with half a row per
+// thread, software-pipelining the next step's TMEM load and max under the exponentials, two
+// warpgroups per CTA with one or two MMA warps (with and without a phase offset).
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "wb_kernels.hpp"
 
@@ -39,11 +48,11 @@ namespace wb {
 namespace {
 
 constexpr int QT = 128;   // queries per softmax warpgroup
-constexpr int NWG = 2;    // query tiles (warpgroups) per CTA, sharing every K/V stage
+constexpr int NWG = 1;    // query tiles (softmax warpgroups) per CTA; two CTAs share an SM instead
 constexpr int KT = 128;   // keys per TMA stage
 constexpr int KS = 64;    // keys per step
 constexpr int DH = 64;
-constexpr int NS = 3;     // K/V stages
+constexpr int NS = 2;     // K/V stages (104 KB of shared memory per CTA would not fit twice with 3)
 constexpr int VROWS = ATTN_VT_HEAD_ROWS;          // 64 head rows + ones row + 15 zero rows
 constexpr int TILE_QK_BYTES = QT * DH * 2;        // 16 KB: 128 rows of 128 bytes
 constexpr int TILE_V_HALF_BYTES = VROWS * 64 * 2; // 10 KB: [80 rows][64 keys]
@@ -54,9 +63,13 @@ constexpr int SMEM_V = SMEM_K + NS * TILE_QK_BYTES;            // NS stages x 2 
 constexpr int SMEM_BAR = SMEM_V + NS * TILE_V_BYTES;
 constexpr int ATTN_SMEM_BYTES = SMEM_BAR + 256;
 static_assert(SMEM_V % 1024 == 0 && TILE_V_HALF_BYTES % 1024 == 0, "swizzle alignment");
-constexpr int MMA_WARP = 4 * NWG, TMA_WARP = 4 * NWG + 1;   // after the 8 softmax warps
-constexpr int ATTN_THREADS = 32 * (4 * NWG + 2);
-constexpr uint32_t TMEM_COLS = 512;
+// after the 8 softmax warps: one MMA-issuing warp PER warpgroup (a thread that issues tcgen05.mma is
+// blocked while the instruction executes, and every mbarrier wait costs ~175 cycles even when already
+// complete: with a single issuing warp those latencies serialised with the other warpgroup's MMAs and
+// set the kernel's pace), then the TMA warp
+constexpr int MMA_WARP = 4 * NWG, TMA_WARP = 5 * NWG;
+constexpr int ATTN_THREADS = 32 * (5 * NWG + 1);
+constexpr uint32_t TMEM_COLS = 256;   // S0 | S1 | O: two CTAs fit the SM's 512 columns
 constexpr uint32_t TMEM_WG_STRIDE = 256;          // per warpgroup: S buffers at +0 and +64 (P over them), O at +128
 constexpr uint32_t TMEM_S = 0, TMEM_O = 128;
 constexpr float RESCALE_LOG2 = 8.0f;              // lazy rescale threshold: P stays below 2^8
@@ -122,7 +135,7 @@ __device__ __forceinline__ float max_chunk(const uint32_t (&s)[32]) {
   return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
 }
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __grid_constant__ CUtensorMap vt_map,
                          const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -156,7 +169,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bar_kfull[i], 1);
       mbar_init(&bar_vfull[i], 1);
-      mbar_init(&bar_free[i], 1);
+      mbar_init(&bar_free[i], NWG);   // one commit per MMA warp
     }
     fence_mbar_init();
   }
@@ -186,8 +199,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
         tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES + TILE_V_HALF_BYTES, &vt_map, &bar_vfull[st], j * KT + 64, vrow);
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ===================== every MMA: the whole warp runs this converged, one elected lane issues =====================
+  } else if (warp >= MMA_WARP && warp < TMA_WARP) {
+    // ===================== the MMAs of one warpgroup: the warp runs this converged, one elected lane issues =====================
+    const int wg = warp - MMA_WARP;
     const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0;
     constexpr uint32_t idesc_s = umma_idesc_f16(QT, KS);      // 128 x 64
     constexpr uint32_t idesc_o = umma_idesc_f16(QT, VROWS);   // 128 x 80
@@ -206,42 +220,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
 #pragma unroll
       for (int k = 0; k < KS / 16; ++k) umma_f16_ts_elect(d, pa + 8 * k, dv + 2 * k, idesc_o, (j | k) != 0);
     };
-    // prologue: the first two score tiles of each warpgroup
+    // prologue: the first two score tiles
     mbar_wait(&bar_kfull[0], 0);
-    for (int wg = 0; wg < NWG; ++wg) {
-      mbar_wait(&bar_q[wg], 0);
-      tc_fence_after();
-      issue_s(wg, 0);
-      umma_commit_elect(&bar_s[wg * 2 + 0]);
-      if (n_steps > 1) {
-        issue_s(wg, 1);
-        umma_commit_elect(&bar_s[wg * 2 + 1]);
-      }
+    mbar_wait(&bar_q[wg], 0);
+    tc_fence_after();
+    issue_s(wg, 0);
+    umma_commit_elect(&bar_s[wg * 2 + 0]);
+    if (n_steps > 1) {
+      issue_s(wg, 1);
+      umma_commit_elect(&bar_s[wg * 2 + 1]);
     }
     for (int j = 0; j < n_steps; ++j) {
       const int J = j >> 1, sb = j & 1;
-      for (int wg = 0; wg < NWG; ++wg) {
-        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 0);
-        mbar_wait(&bar_p[wg * 2 + sb], (j >> 1) & 1);   // P_j[wg] in TMEM, S_j[wg] consumed
-        if (wg == 0 && sb == 0) mbar_wait(&bar_vfull[J % NS], (J / NS) & 1);
-        tc_fence_after();
-        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 1);
-        issue_o(wg, j);
-        umma_commit_elect(&bar_o[wg]);
-        if (j == n_steps - 1) umma_commit_elect(&bar_done[wg]);
-        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 2);
-        if (j + 2 < n_steps) {
-          const int J2 = (j + 2) >> 1;
-          if (wg == 0 && sb == 0) {
-            mbar_wait(&bar_kfull[J2 % NS], (J2 / NS) & 1);
-            tc_fence_after();
-          }
-          issue_s(wg, j + 2);   // overwrites S_j / P_j: ordered behind the P.V MMAs above by the tensor pipe
-          umma_commit_elect(&bar_s[wg * 2 + sb]);
+      ATTN_TRACE(512 + (j * 2 + wg) * 4 + 0);
+      mbar_wait(&bar_p[wg * 2 + sb], (j >> 1) & 1);   // P_j in TMEM, S_j consumed
+      if (sb == 0) mbar_wait(&bar_vfull[J % NS], (J / NS) & 1);
+      tc_fence_after();
+      ATTN_TRACE(512 + (j * 2 + wg) * 4 + 1);
+      issue_o(wg, j);
+      umma_commit_elect(&bar_o[wg]);
+      if (j == n_steps - 1) umma_commit_elect(&bar_done[wg]);
+      ATTN_TRACE(512 + (j * 2 + wg) * 4 + 2);
+      if (j + 2 < n_steps) {
+        const int J2 = (j + 2) >> 1;
+        if (sb == 0) {
+          mbar_wait(&bar_kfull[J2 % NS], (J2 / NS) & 1);
+          tc_fence_after();
         }
-        ATTN_TRACE(512 + (j * 2 + wg) * 4 + 3);
+        issue_s(wg, j + 2);   // overwrites S_j / P_j: ordered behind the P.V MMAs above by the tensor pipe
+        umma_commit_elect(&bar_s[wg * 2 + sb]);
       }
-      // both halves of stage J have been read by every MMA issued so far: free once they retire
+      ATTN_TRACE(512 + (j * 2 + wg) * 4 + 3);
+      // this warpgroup's MMAs on both halves of stage J are issued: free once they (and the other
+      // warpgroup's) retire
       if (sb == 1 || j == n_steps - 1) umma_commit_elect(&bar_free[J % NS]);
     }
   } else {
@@ -389,6 +400,8 @@ cudaError_t launch_attention(const AttnProblem& p, cudaStream_t st) {
   a.n_steps = (p.T + KS - 1) / KS;
   a.out = p.out;
   a.scale_log2 = p.scale * 1.4426950408889634f;
+
+
   a.dbg = p.dbg;
   dim3 grid((p.T + NWG * QT - 1) / (NWG * QT), p.H, p.B);
   attention_tcgen05_kernel<<<grid, ATTN_THREADS, ATTN_SMEM_BYTES, st>>>(p.qk_map, p.vt_map, a);
