@@ -82,6 +82,17 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def gemm_traffic(arch: str, B: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_gemm_traffic.json), or None when no capture exists for this workload."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        e = d.get(f"{arch}_b{B}")
+        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "unit": "bytes", "source": e["source"]} if e else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
 
@@ -417,7 +428,7 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
             "roofline": {
                 "kernel": "gemm_f16_tcgen05_kernel (all tile widths; conv stem, QKV, out-proj, MLP, cross-KV)",
                 "bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": gemm_tf / peak_tf if peak_tf else None, "traffic": None,
+                "frac": gemm_tf / peak_tf if peak_tf else None, "traffic": gemm_traffic(arch, B),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})",
                 "launches_per_step": gemm_n / K, "avg_launch_us": gemm_us / gemm_n if gemm_n else None,
                 "share_of_step": shares.get("gemm"),
@@ -458,7 +469,7 @@ def main():
     ap.add_argument("--arch", default="base")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--samples", type=int, default=480000)
-    ap.add_argument("--cpu-segments", type=int, default=4)
+    ap.add_argument("--cpu-segments", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decoder", action="store_true", help="skip the decoder tokens/sec leg")
     ap.add_argument("--dec-arch", default="small")
