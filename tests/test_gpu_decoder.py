@@ -111,3 +111,30 @@ def test_tiny_decode_30s(pkg, pyoracle, model_path):
     rt, rm = orcs[0].decode_greedy(prompt, 16)
     assert _check_greedy(toks[0], lens[0], rt, rm) >= 1
     ctx.close()
+
+
+@pytest.mark.parametrize("arch", ["small.2l", "medium.2l", "large-v3.2l"])
+def test_full_width_two_layer_pipeline(pkg, pyoracle, model_path, arch):
+    """configs[2..4] widths (d = 768 / 1024 / 1280; 12 / 16 / 20 heads; large-v3's 128 mel bins and
+    51866-entry vocabulary) at 2 + 2 layers: mel + encode + cross K/V + logits + greedy against the
+    oracle on one 30 s clip, two sequences in the batch."""
+    from whisper_rs_b200 import api
+    ctx, orcs = _setup(pkg, pyoracle, model_path, arch, 2, 480000)
+    assert ctx.n_mels == (128 if arch.startswith("large") else 80)
+    for s in range(2):
+        renc = orcs[s].encode(0)
+        assert rel_l2(ctx.encoder_out(s), renc) < 1e-2, (arch, s)
+        k, v = ctx.cross_kv(s, ctx.n_text_layer - 1)
+        rk, rv = orcs[s].cross_kv(ctx.n_text_layer - 1)
+        assert rel_l2(k, rk) < 1e-2 and rel_l2(v, rv) < 1e-2
+    prompt = [ctx.token_sot]
+    api.whisper_decode(ctx, np.array([prompt, prompt], dtype=np.int32), 0)
+    for s in range(2):
+        assert rel_l2(ctx.logits(s), orcs[s].decode(prompt, 0)) < LOGIT_TOL, (arch, s)
+    toks, marg, lens = api.whisper_decode_greedy(ctx, prompt, 12, n_seqs=2)
+    agree = 0
+    for s in range(2):
+        rt, rm = orcs[s].decode_greedy(prompt, 12)
+        agree += _check_greedy(toks[s], lens[s], rt, rm)
+    assert agree >= 2
+    ctx.close()

@@ -61,9 +61,14 @@ ARCHS: Dict[str, HParams] = {
     "small": HParams(51864, 1500, 768, 12, 12, 448, 768, 12, 12, 80, 1),
     "medium": HParams(51864, 1500, 1024, 16, 24, 448, 1024, 16, 24, 80, 1),
     "large-v3": HParams(51866, 1500, 1280, 20, 32, 448, 1280, 20, 32, 128, 1),
+    # full-width, 2-layer variants: every tile shape / head count / mel width of the big models at a
+    # depth the CPU oracle checks in seconds
+    "small.2l": HParams(51864, 1500, 768, 12, 2, 448, 768, 12, 2, 80, 1),
+    "medium.2l": HParams(51864, 1500, 1024, 16, 2, 448, 1024, 16, 2, 80, 1),
+    "large-v3.2l": HParams(51866, 1500, 1280, 20, 2, 448, 1280, 20, 2, 128, 1),
 }
 ARCH_SEED_INDEX = {"tiny": 0, "base": 1, "small": 2, "medium": 3, "large-v3": 4,
-                   "micro": 7, "tiny.ml": 8}
+                   "micro": 7, "tiny.ml": 8, "small.2l": 9, "medium.2l": 10, "large-v3.2l": 11}
 
 
 def tensor_table(hp: HParams) -> List[Tuple[str, Tuple[int, ...], str]]:
