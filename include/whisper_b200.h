@@ -117,6 +117,13 @@ int wb_logits_read(wb_ctx* ctx, int seq, float* out);             /* [n_vocab] f
 int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_new, int eot,
                      int n_seqs, int32_t* out_tokens, float* out_margin, int32_t* out_len);
 
+/* WhisperVocab::id_to_token (544) incl. the placeholder names of ids the file has no text for
+ * (442-467).  Returns the token's byte length (the copy is truncated to cap-1 and NUL-terminated),
+ * negative on a bad id.  wb_tokens_to_text concatenates the text tokens (ids below eot) of a
+ * greedy result and skips the special / timestamp ids. */
+int wb_token_text(const wb_ctx* ctx, int32_t id, char* out, size_t cap);
+int wb_tokens_to_text(const wb_ctx* ctx, const int32_t* ids, int n, char* out, size_t cap);
+
 int wb_sync(wb_ctx* ctx);                                         /* wait for the handle's stream */
 int wb_timings_get(const wb_ctx* ctx, wb_timings* out);           /* t_*_us 334-339 */
 const char* wb_last_error(const wb_ctx* ctx);                     /* WsError Display text (52-71); ctx may be NULL */

@@ -95,3 +95,27 @@ def test_capacity_errors(pkg, model_path):
         api.whisper_pcm_to_mel(ctx, np.zeros(480001 * 2, np.float32))
     assert e.value.variant == "NotEnoughSpace"
     ctx.close()
+
+
+def test_vocab_text_and_placeholder_names(pkg, model_path, tmp_path):
+    """id_to_token (src/main.rs:544) and the names the reference gives ids the file has no text for
+    (442-467), on a multilingual-size vocabulary whose file holds fewer entries than hparams.n_vocab."""
+    from whisper_rs_b200 import api
+    import dataclasses
+    hp = dataclasses.replace(pkg.ggml_file.ARCHS["micro"], n_vocab=51865)
+    path = str(tmp_path / "ggml-micro-ml.bin")
+    pkg.ggml_file.write_model(path, hp, seed=3, n_vocab_file=50257)
+    ctx = api.WhisperContext.new(path, max_segments=1, decode_capacity=False)
+    assert ctx.token_eot == 50257 and ctx.token_sot == 50258 and ctx.token_beg == 50364   # +1: multilingual (433-440)
+    assert ctx.token_text(0) == b"t0" and ctx.token_text(50256) == b"t50256"
+    assert ctx.token_text(ctx.token_eot) == b"[_EOT_]"
+    assert ctx.token_text(ctx.token_sot) == b"[_SOT_]"
+    assert ctx.token_text(ctx.token_prev) == b"[_PREV_]"
+    assert ctx.token_text(ctx.token_not) == b"[_NOT_]"
+    assert ctx.token_text(ctx.token_beg) == b"[_BEG_]"
+    assert ctx.token_text(ctx.token_beg + 5) == b"[_TT_5]"
+    assert ctx.token_text(50300) == b"[_extra_token_50300]"
+    assert ctx.tokens_to_text([ctx.token_sot, 5, 17, ctx.token_beg + 3, 9, ctx.token_eot]) == b"t5t17t9"
+    with pytest.raises(api.WsError):
+        ctx.token_text(51865)
+    ctx.close()

@@ -139,6 +139,21 @@ class WhisperContext:
         _check(cabi.lib().wb_logits_read(self._h, seq, _f32p(out)), self._h)
         return out
 
+    def token_text(self, token_id: int) -> bytes:
+        """WhisperVocab::id_to_token (src/main.rs:544)."""
+        buf = C.create_string_buffer(256)
+        n = cabi.lib().wb_token_text(self._h, int(token_id), buf, 256)
+        if n < 0:
+            raise WsError(n, "token id out of range")
+        return buf.raw[:min(n, 255)]
+
+    def tokens_to_text(self, ids) -> bytes:
+        a = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+        n = cabi.lib().wb_tokens_to_text(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        cabi.lib().wb_tokens_to_text(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, buf, n + 1)
+        return buf.raw[:n]
+
     def timings(self) -> dict:
         t = cabi.WbTimings()
         _check(cabi.lib().wb_timings_get(self._h, C.byref(t)), self._h)

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
     L.wb_pcm_to_mel_device.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
     L.wb_pcm16_to_mel.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
     L.wb_pcm_prefetch.argtypes = [vp, C.c_void_p, C.c_size_t]
+    L.wb_token_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_size_t]
+    L.wb_tokens_to_text.argtypes = [vp, C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.c_size_t]
     L.wb_mel_dims.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.wb_mel_read.argtypes = [vp, C.c_int, f32p, C.c_size_t]
     L.wb_mel_write.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int]

@@ -520,6 +520,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   ctx->num_sms = prop.multiProcessorCount;
   ctx->hp = hp;
   memcpy(ctx->special, mv.special, sizeof(mv.special));
+  ctx->vocab = mv.vocab;
   ctx->time_kernels = cfg.reserved[0] != 0;
   auto bail = [&](int code) {
     std::string m = ctx->err;
@@ -633,6 +634,31 @@ int wb_get_special_tokens(const wb_ctx* ctx, int32_t out[8]) {
   if (!ctx || !out) return WB_ERR_UNEXPECTED;
   memcpy(out, ctx->special, 32);
   return WB_OK;
+}
+
+int wb_token_text(const wb_ctx* ctx, int32_t id, char* out, size_t cap) {
+  if (!ctx || id < 0 || (size_t)id >= ctx->vocab.size()) return WB_ERR_UNEXPECTED;
+  const std::string& w = ctx->vocab[(size_t)id];
+  if (out && cap) {
+    const size_t n = w.size() < cap - 1 ? w.size() : cap - 1;
+    memcpy(out, w.data(), n);
+    out[n] = 0;
+  }
+  return (int)w.size();
+}
+
+int wb_tokens_to_text(const wb_ctx* ctx, const int32_t* ids, int n, char* out, size_t cap) {
+  if (!ctx || (!ids && n > 0) || n < 0) return WB_ERR_UNEXPECTED;
+  // text tokens are the ids below eot (557-575): specials, language / task and timestamp ids are skipped
+  std::string s;
+  for (int i = 0; i < n; ++i)
+    if (ids[i] >= 0 && ids[i] < ctx->special[0] && (size_t)ids[i] < ctx->vocab.size()) s += ctx->vocab[(size_t)ids[i]];
+  if (out && cap) {
+    const size_t m = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(out, s.data(), m);
+    out[m] = 0;
+  }
+  return (int)s.size();
 }
 
 int wb_sync(wb_ctx* ctx) {

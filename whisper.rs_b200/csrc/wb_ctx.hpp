@@ -54,6 +54,7 @@ struct wb_ctx {
   std::string err;
   wb::ModelHParams hp{};
   int32_t special[8]{};
+  std::vector<std::string> vocab;   // id_to_token (src/main.rs:544)
   std::vector<void*> allocs;
 
   // ---- weights

@@ -39,6 +39,7 @@ struct ModelFileView {
   int filt_n_mel = 0, filt_n_fft = 0;
   const float* filters = nullptr;
   int32_t n_vocab_file = 0;
+  std::vector<std::string> vocab;   // id_to_token (544): file entries + the reference's names for extra ids (442-467)
   int32_t special[8] = {50256, 50257, 50360, 50361, 50362, 50363, 50358, 50359};   // 557-575
   std::unordered_map<std::string, HostTensor> tensors;
 };
@@ -148,15 +149,30 @@ inline int parse_model_file(const char* path, ModelFileView& mv, std::string& er
   mv.filters = reinterpret_cast<const float*>(p);
   p += (size_t)mv.filt_n_mel * mv.filt_n_fft * 4;
   if (!rd32(mv.n_vocab_file) || mv.n_vocab_file < 0) { err = eof_msg; return WB_ERR_IO; }
-  for (int i = 0; i < mv.n_vocab_file; ++i) {   // token text is not needed on the hot path: skip
+  mv.vocab.reserve((size_t)(hp.n_vocab > mv.n_vocab_file ? hp.n_vocab : mv.n_vocab_file));
+  for (int i = 0; i < mv.n_vocab_file; ++i) {   // WhisperVocab::load (578-589): u32 length + bytes per token
     int32_t len = 0;
     if (!rd32(len) || len < 0 || !need((size_t)len)) { err = eof_msg; return WB_ERR_IO; }
+    mv.vocab.emplace_back(reinterpret_cast<const char*>(p), (size_t)len);
     p += len;
   }
   // special-token fix-up (433-440).  The reference tests n_vocab == 51865 only (594-596);
   // large-v3 (51866) is multilingual as well, so >= is used.
   if (hp.n_vocab >= 51865)
     for (int i = 0; i < 6; ++i) mv.special[i] += 1;
+  // ids the file has no text for get the reference's placeholder names (442-467)
+  for (int i = mv.n_vocab_file; i < hp.n_vocab; ++i) {
+    const int eot = mv.special[0], sot = mv.special[1], prev = mv.special[2], tnot = mv.special[4], beg = mv.special[5];
+    std::string w;
+    if (i > beg) w = "[_TT_" + std::to_string(i - beg) + "]";
+    else if (i == eot) w = "[_EOT_]";
+    else if (i == sot) w = "[_SOT_]";
+    else if (i == prev) w = "[_PREV_]";
+    else if (i == tnot) w = "[_NOT_]";
+    else if (i == beg) w = "[_BEG_]";
+    else w = "[_extra_token_" + std::to_string(i) + "]";
+    mv.vocab.push_back(w);
+  }
 
   std::unordered_map<std::string, detail::Expect> table;
   detail::expect_table(hp, table);

@@ -75,6 +75,8 @@ extern "C" {
     pub fn wb_logits_read(ctx: *mut wb_ctx, seq: c_int, out: *mut f32) -> c_int;
     pub fn wb_decode_greedy(ctx: *mut wb_ctx, prompt: *const i32, n_prompt: c_int, max_new: c_int, eot: c_int,
                             n_seqs: c_int, out_tokens: *mut i32, out_margin: *mut f32, out_len: *mut i32) -> c_int;
+    pub fn wb_token_text(ctx: *const wb_ctx, id: i32, out: *mut c_char, cap: usize) -> c_int;
+    pub fn wb_tokens_to_text(ctx: *const wb_ctx, ids: *const i32, n: c_int, out: *mut c_char, cap: usize) -> c_int;
     pub fn wb_sync(ctx: *mut wb_ctx) -> c_int;
     pub fn wb_timings_get(ctx: *const wb_ctx, out: *mut wb_timings) -> c_int;
     pub fn wb_last_error(ctx: *const wb_ctx) -> *const c_char;
