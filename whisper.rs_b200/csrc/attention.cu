@@ -178,6 +178,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == TMA_WARP) {
     // ===================== TMA loads, one thread =====================
@@ -404,8 +406,7 @@ cudaError_t launch_attention(const AttnProblem& p, cudaStream_t st) {
 
   a.dbg = p.dbg;
   dim3 grid((p.T + NWG * QT - 1) / (NWG * QT), p.H, p.B);
-  attention_tcgen05_kernel<<<grid, ATTN_THREADS, ATTN_SMEM_BYTES, st>>>(p.qk_map, p.vt_map, a);
-  return cudaGetLastError();
+  return launch_pdl(attention_tcgen05_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM_BYTES, st, p.qk_map, p.vt_map, a);
 }
 
 }  // namespace wb

@@ -129,6 +129,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
   cluster_sync_all();   // both CTAs' barriers and TMEM exist before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   const int num_kb = (args.K + BK - 1) / BK;
   const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
@@ -423,13 +425,15 @@ cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaSt
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue under the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN>, g.a_map, g.w_map, *g.out_map,
                             g.res_map ? *g.res_map : *g.out_map, a);
 }

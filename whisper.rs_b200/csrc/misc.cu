@@ -16,6 +16,8 @@ namespace {
 __global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
                                   const long long* __restrict__ offsets, int Tm, __half* __restrict__ out) {
   __shared__ float tile[32][33];
+  pdl_wait();
+  pdl_launch_dependents();
   const int seg = blockIdx.z;
   const int clip = clip_ids ? clip_ids[seg] : 0;
   const long long off = offsets ? offsets[seg] : 0;
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long in_row_stride, const float* __restrict__ w,
                  const float* __restrict__ b, int rows, int d, __half* __restrict__ out_f16,
                  float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int row0 = warp * RPW;
@@ -150,18 +154,18 @@ __global__ void abs_sum_f16_kernel(const __half* __restrict__ x, int rows, int c
 cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int* clip_ids, const long long* offsets,
                               int n_seg, int Tm, __half* out, cudaStream_t st) {
   dim3 grid((Tm + 31) / 32, (n_mel + 31) / 32, n_seg);
-  mel_window_kernel<<<grid, dim3(32, 8), 0, st>>>(mel, n_mel, n_len, clip_ids, offsets, Tm, out);
-  return cudaGetLastError();
+  return launch_pdl(mel_window_kernel, grid, dim3(32, 8), 0, st, mel, n_mel, n_len, clip_ids, offsets, Tm, out);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d, __half* out_f16,
-                             float* out_f32, cudaStream_t st, long long in_row_stride) {
+                             float* out_f32, cudaStream_t st, long long in_row_stride, bool pdl) {
   if (d % 4 != 0 || d > 128 * LN_MAX_V4) return cudaErrorInvalidValue;
   if (in_row_stride <= 0) in_row_stride = d;
   const int nv = (d / 4 + 31) / 32;   // float4 per lane
   auto go = [&](auto kernel, int rpw) {
     const int warps = (rows + rpw - 1) / rpw;
-    kernel<<<(warps + 7) / 8, 256, 0, st>>>(x, in_row_stride, w, b, rows, d, out_f16, out_f32);
+    if (pdl) launch_pdl(kernel, dim3((warps + 7) / 8), dim3(256), 0, st, x, in_row_stride, w, b, rows, d, out_f16, out_f32);
+    else kernel<<<(warps + 7) / 8, 256, 0, st>>>(x, in_row_stride, w, b, rows, d, out_f16, out_f32);
   };
   // one row per warp: measured on B200 (base, 24000 rows of 512), 2 and 4 rows per warp in flight were
   // slower (250 vs 224 us per step over 13 launches) -- the rows mostly come out of L2, where the previous

@@ -362,6 +362,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (allocate
+// TMEM, initialise barriers, prefetch descriptors) while the previous kernel in the stream is still
+// draining; pdl_wait() blocks until that kernel has completed and its writes are visible, and must
+// precede the first access to anything it produced.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -903,7 +903,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     const EncLayer& l = ctx->enc[il];
     {   // E4: attn_ln
       LaunchTimer t(ctx, "layernorm");
-      WB_CK(launch_layernorm(ctx->x, l.attn_ln_w, l.attn_ln_b, M, d, ctx->ln_out, nullptr, st));
+      WB_CK(launch_layernorm(ctx->x, l.attn_ln_w, l.attn_ln_b, M, d, ctx->ln_out, nullptr, st, 0, true));
     }
     {   // E5 + E6: fused Q|K|V projection, F16 repack; V transposed, time contiguous (1891-1920)
       GemmEpilogue e;
@@ -933,7 +933,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     }
     {   // E9: mlp_ln, fc1 + bias + GELU, fc2 + bias + residual (1948-1968)
       LaunchTimer t(ctx, "layernorm");
-      WB_CK(launch_layernorm(ctx->x, l.mlp_ln_w, l.mlp_ln_b, M, d, ctx->ln_out, nullptr, st));
+      WB_CK(launch_layernorm(ctx->x, l.mlp_ln_w, l.mlp_ln_b, M, d, ctx->ln_out, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
@@ -956,7 +956,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   }
   {   // E11: ln_post (1980-1984): f32 copy for read-back, F16 copy as the cross-KV GEMM operand
     LaunchTimer t(ctx, "layernorm");
-    WB_CK(launch_layernorm(ctx->x, ctx->ln_post_w, ctx->ln_post_b, M, d, ctx->enc_f16, ctx->enc_out, st));
+    WB_CK(launch_layernorm(ctx->x, ctx->ln_post_w, ctx->ln_post_b, M, d, ctx->enc_f16, ctx->enc_out, st, 0, true));
   }
   if (chk && (rc = probe_f32(3 + L, ctx->enc_out, (long long)T * d, (long long)T * d))) return rc;
   if (Lt > 0) {   // E12: cross-attention K/V of all text layers in one GEMM (1990-2030)

@@ -6,7 +6,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace wb {
+
+// Launch with programmatic stream serialisation (see pdl_wait() in ptx.cuh): the kernel's prologue
+// overlaps the tail of the previous kernel in the stream.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 // ---- TMA descriptors (cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint so the
 // library has no link-time dependency on libcuda) ------------------------------------------------
@@ -112,7 +131,8 @@ cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int*
                               const long long* offsets, int n_seg, int Tm, __half* out, cudaStream_t st);
 // galois_norm + repeat/mul/add (1781-1785, 1882-1886): rows of d, f32 in; f16 and/or f32 out
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d,
-                             __half* out_f16, float* out_f32, cudaStream_t st, long long in_row_stride = 0);
+                             __half* out_f16, float* out_f32, cudaStream_t st, long long in_row_stride = 0,
+                             bool pdl = false);
 // sum|x| probes (1836-1849): out[seg] = sum over that segment's elements
 cudaError_t launch_abs_sum_f32(const float* x, long long per_seg, long long seg_stride, int n_seg, double* out,
                                cudaStream_t st);
