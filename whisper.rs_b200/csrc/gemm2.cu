@@ -55,7 +55,12 @@ struct Gemm2Args {
   int out_slab_cols;       // > 0: output column n lives in slab n / C at column n % C (out_map's third dimension)
   __half* vt_out;          // columns >= vt_col0 go to the transposed V buffer (see GemmEpilogue)
   int vt_col0, vt_heads, vt_head_rows, vt_ld, vt_T;
+  long long* dbg;          // optional clock64() trace (CTA 0): [0,256) MMA warp, [256,1024) epilogue warp 4
 };
+#define G2_TRACE(cond, slot)                                   \
+  do {                                                         \
+    if ((cond) && (slot) < 1024) args.dbg[(slot)] = clock64(); \
+  } while (0)
 
 template <int BN>
 struct Cfg {
@@ -84,7 +89,10 @@ __device__ __forceinline__ Item item_coord(const Gemm2Args& a, int item) {
   return t;
 }
 
-template <int BN>
+// Epilogue variants are compile-time (F16 or f32 output, GELU, column scale, f32 residual): as run-time
+// flags the compiler predicated the unused paths off instruction by instruction -- the epilogue warps
+// still issued them, and at K = 512 the epilogue, not the tensor pipe, set the tile rate.
+template <int BN, bool F16O, bool GELU, bool CS, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                          const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap res_map,
@@ -110,7 +118,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
     prefetch_tmap(&a_map);
     prefetch_tmap(&w_map);
     prefetch_tmap(&out_map);
-    if (args.has_res) prefetch_tmap(&res_map);
+    if (RES) prefetch_tmap(&res_map);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -159,8 +167,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; the warp stays converged, one elected lane issues) =====================
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -168,8 +176,11 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
       for (int item = item0; item < args.total_items; item += item_step, ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (t >> 1) & 1;
+        const bool trm = args.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        G2_TRACE(trm, t * 4 + 0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
+        G2_TRACE(trm, t * 4 + 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -178,9 +189,12 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           const uint64_t da = umma_desc_k_sw128(sa);
           const uint64_t db = umma_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_cg2(&empty_bar[stage], 3);
-          if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc], 3);
+          for (int k = 0; k < BK / 16; ++k) umma_f16_ss_cg2_elect(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_cg2_elect(&empty_bar[stage], 3);
+          if (kb == num_kb - 1) {
+            umma_commit_cg2_elect(&tmem_full[acc], 3);
+            G2_TRACE(trm, t * 4 + 2);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -197,12 +211,12 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
     uint64_t* my_res_bar = res_bar + ew * NBUF;
     float* my_bias = bias_stage + ew * 2 * BN;
     float* my_cs = my_bias + BN;
-    const bool f16o = args.out_f16 != 0;
-    const int cw = f16o ? 64 : 32;                       // chunk width in columns (128 bytes of output)
+    constexpr bool f16o = F16O;
+    constexpr int cw = f16o ? 64 : 32;                   // chunk width in columns (128 bytes of output)
     const int n_chunks_tile = BN / cw;
     const int my_nch = (n_chunks_tile - half + 1) / 2;   // chunks half, half+2, ...
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-    const bool has_cs = args.colscale != nullptr || args.scale != 1.0f;
+    constexpr bool has_cs = CS;
     const int sw = lane & 7;
 
     // coordinates of this warp's chunk number `ci` (counted over all of its tiles)
@@ -226,7 +240,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
     };
 
     int ci = 0;   // chunks this warp has started
-    if (args.has_res && my_nch > 0 && lane == 0) issue_residual(0);
+    if (RES && my_nch > 0 && lane == 0) issue_residual(0);
     int t = 0;
     for (int item = item0; item < args.total_items; item += item_step, ++t) {
       const Item it = item_coord(args, item);
@@ -249,7 +263,10 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           }
         }
       }
+      const bool tre = args.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+      G2_TRACE(tre, 256 + t * 16 + 0);
       mbar_wait(&tmem_full[acc], acc_phase);
+      G2_TRACE(tre, 256 + t * 16 + 1);
       __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the spin
       tc_fence_after();
 #pragma unroll
@@ -285,6 +302,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           if (f16o) tmem_ld_32x32b_x32(t_row + col + 32, r1);
           tmem_ld_wait();
         }
+        G2_TRACE(tre, 256 + t * 16 + 2 + k * 4);   // chunk k: accumulator in registers
         if (last_chunk) {   // this warp is done with the accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -305,7 +323,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
               const float4 cv = c4[g];
               x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
             }
-            if (args.gelu) {
+            if (GELU) {
               x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
             }
             r0[4 * g] = __float_as_uint(x0); r0[4 * g + 1] = __float_as_uint(x1);
@@ -321,7 +339,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
                 const float4 cv = c4[8 + g];
                 x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
               }
-              if (args.gelu) {
+              if (GELU) {
                 x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
               }
               r1[4 * g] = __float_as_uint(x0); r1[4 * g + 1] = __float_as_uint(x1);
@@ -350,7 +368,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           continue;
         }
 
-        if (args.has_res) {
+        if (RES) {
           // ---- + residual: its box was TMA-loaded into this buffer one chunk ago
           mbar_wait(&my_res_bar[buf], (ci / NBUF) & 1);
 #pragma unroll
@@ -391,13 +409,15 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
                            : "memory");
           }
         }
+        G2_TRACE(tre, 256 + t * 16 + 3 + k * 4);   // math + shared-memory box written
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
         __syncwarp();
+        G2_TRACE(tre, 256 + t * 16 + 4 + k * 4);   // fenced
         if (lane == 0) {
           if (args.out_slab_cols > 0) tma_store_3d(&out_map, sbuf, n0 % args.out_slab_cols, m_row0, n0 / args.out_slab_cols);
           else tma_store_3d(&out_map, sbuf, n0, m_row0, it.b);
           bulk_commit_group();
-          if (args.has_res) {
+          if (RES) {
             // prefetch the next chunk's residual into the other buffer once the store that last
             // read it (chunk ci - 1) has drained; the store just issued may stay in flight
             bulk_wait_group_read<1>();
@@ -405,6 +425,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           }
         }
         __syncwarp();
+        G2_TRACE(tre, 256 + t * 16 + 5 + k * 4);   // store issued (+ residual prefetch)
       }
     }
     if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the stores' reads
@@ -418,8 +439,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
   }
 }
 
-template <int BN>
-cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
+template <int BN, bool F16O, bool GELU, bool CS, bool RES>
+cudaError_t launch_one(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -434,25 +455,41 @@ cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaSt
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN>, g.a_map, g.w_map, *g.out_map,
+  // the kernel's opt-in to > 48 KB of dynamic shared memory, once per instantiation
+  static cudaError_t attr_err = cudaFuncSetAttribute(gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+  if (attr_err != cudaSuccess) return attr_err;
+  return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES>, g.a_map, g.w_map, *g.out_map,
                             g.res_map ? *g.res_map : *g.out_map, a);
 }
 
 template <int BN>
-bool set_attr(const char** err) {
-  cudaError_t e = cudaFuncSetAttribute(gemm2_f16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<BN>::SMEM_BYTES);
-  if (e != cudaSuccess) {
-    *err = cudaGetErrorString(e);
-    return false;
-  }
-  return true;
+cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
+  const bool f16 = a.out_f16 != 0, gelu = a.gelu != 0, cs = a.colscale != nullptr || a.scale != 1.0f, res = a.has_res != 0;
+  if (f16 && res) return cudaErrorInvalidValue;
+#define WB_G2_CASE(F, G, C, R) \
+  if (f16 == F && gelu == G && cs == C && res == R) return launch_one<BN, F, G, C, R>(g, a, grid, st)
+  WB_G2_CASE(true, false, false, false);
+  WB_G2_CASE(true, true, false, false);
+  WB_G2_CASE(true, false, true, false);
+  WB_G2_CASE(true, true, true, false);
+  WB_G2_CASE(false, false, false, false);
+  WB_G2_CASE(false, true, false, false);
+  WB_G2_CASE(false, false, true, false);
+  WB_G2_CASE(false, true, true, false);
+  WB_G2_CASE(false, false, false, true);
+  WB_G2_CASE(false, true, false, true);
+  WB_G2_CASE(false, false, true, true);
+  WB_G2_CASE(false, true, true, true);
+#undef WB_G2_CASE
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
 bool gemm2_setup_attributes(const char** err) {
-  return set_attr<256>(err) && set_attr<192>(err) && set_attr<128>(err) && set_attr<64>(err);
+  (void)err;   // each instantiation opts in to its shared-memory size at its first launch (launch_one)
+  return true;
 }
 
 // pair tile width: widest of 256 / 192 / 128 / 64 that divides N; 0 = not eligible (use gemm.cu)
@@ -488,6 +525,7 @@ cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
   a.vt_head_rows = g.epi.vt_head_rows;
   a.vt_ld = g.epi.vt_ld;
   a.vt_T = g.epi.vt_T;
+  a.dbg = g.dbg;
   if (a.total_items <= 0) return cudaSuccess;
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (a.total_items < max_pairs ? a.total_items : max_pairs);

@@ -223,6 +223,29 @@ __device__ __forceinline__ void umma_f16_ss_cg2(uint32_t tmem_d, uint64_t desc_a
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// warp-converged forms (see umma_f16_ss_elect): one elected lane issues, operands stay uniform
+__device__ __forceinline__ void umma_f16_ss_cg2_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(

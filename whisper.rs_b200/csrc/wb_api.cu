@@ -186,9 +186,12 @@ static bool force_gemm1() {
   return v;
 }
 
+static long long* g_gemm_trace = nullptr;   // developer aid: set by wb_dbg_gemm when WB_GEMM_TRACE is given
+
 int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const Linear& l, GemmEpilogue epi,
              const char* family, const CUtensorMap* out_map, const CUtensorMap* res_map, int res_bcast) {
   GemmProblem g;
+  g.dbg = g_gemm_trace;
   g.a_map = a_map;
   g.M_rows = M_rows;
   g.batch = batch;
@@ -1143,7 +1146,23 @@ int wb_dbg_gemm(wb_ctx* ctx, int M, int N, int K, const uint16_t* a_f16, const u
     cleanup();
     return WB_ERR_TENSOR_OP;
   }
+  const char* trace_path = getenv("WB_GEMM_TRACE");   // per-phase clock64() trace of CTA 0 (tools/gemm_trace.py)
+  if (trace_path) {
+    DBG_CK(cudaMalloc(&g_gemm_trace, 1024 * sizeof(long long)));
+    DBG_CK(cudaMemset(g_gemm_trace, 0, 1024 * sizeof(long long)));
+  }
   rc = run_gemm(ctx, ma, M, 1, l, ep, "dbg_gemm", &mo, dR ? &mr : nullptr, 0);
+  if (trace_path) {
+    cudaStreamSynchronize(ctx->stream);
+    std::vector<long long> h(1024);
+    cudaMemcpy(h.data(), g_gemm_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(g_gemm_trace);
+    g_gemm_trace = nullptr;
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int i = 0; i < 1024; ++i) fprintf(f, "%lld\n", h[i]);
+      fclose(f);
+    }
+  }
   if (rc == WB_OK) {
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, WB_ERR_TENSOR_OP, "gemm kernel", e);

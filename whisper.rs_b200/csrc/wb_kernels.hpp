@@ -83,6 +83,7 @@ struct GemmProblem {
   const CUtensorMap* out_map = nullptr;
   const CUtensorMap* res_map = nullptr;
   int res_bcast = 0;
+  long long* dbg = nullptr;   // optional clock64() trace of pair 0 (tools/gemm_trace.py); nullptr in production
 };
 cudaError_t launch_gemm(const GemmProblem& g, int num_sms, cudaStream_t st);
 int gemm_pick_bn(int N);
