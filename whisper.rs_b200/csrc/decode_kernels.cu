@@ -59,6 +59,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
 // D1: x[s][i][:] = d_te[tok[s][i]][:] + d_pe[n_past + i][:]
 __global__ void embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
                              int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   const int row = blockIdx.x;   // s * n_tok + i
   const int i = row % n_tok;
   const int tok = tokens[row];
@@ -81,6 +83,8 @@ constexpr int SELF_MAX_CTX = 448 + 64;
 __global__ void __launch_bounds__(SELF_THREADS)
 decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restrict__ kc, __half* __restrict__ vc,
                         int n_tok, const int* __restrict__ n_past_p, int n_text_ctx, __half* __restrict__ out) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   __shared__ float sc[SELF_MAX_CTX];
   __shared__ float red[SELF_THREADS / 32];
   __shared__ float opart[SELF_THREADS / 32][4][DH];
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(CROSS_THREADS, 3)
 decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
                          long long ld, int n_tok, int T, int span, __half* __restrict__ out,
                          float* __restrict__ part_o, float* __restrict__ part_ml, int n_split) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   __shared__ float sc[CROSS_MAX_SPAN];
   __shared__ float red[CROSS_THREADS / 32];
   __shared__ float opart[CROSS_THREADS / 32][4][DH];
@@ -267,6 +273,8 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
 // merge split partials: out = sum_s w_s o_s, w_s = l_s e^(m_s - m) / sum_s' l_s' e^(m_s' - m)
 __global__ void cross_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int n_split,
                                      int d, __half* __restrict__ out) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   const int h = blockIdx.x, row = blockIdx.y, H = gridDim.x, c = threadIdx.x;
   const size_t p0 = ((size_t)row * H + h) * n_split;
   float m = -INFINITY;
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ next_tok, float* __restrict__ margin_out,
               int* __restrict__ out_tokens, float* __restrict__ out_margin, int* __restrict__ out_len,
               int* __restrict__ done, int max_new, const int* __restrict__ step_p, int eot) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   __shared__ Top2 sh[32];
   const int s = blockIdx.x;
   const float* lg = logits + (size_t)s * n_vocab;
@@ -372,6 +382,8 @@ constexpr int DL_ROWS = 16;       // weight rows (output features) per CTA
 
 __global__ void __launch_bounds__(DL_THREADS)
 decode_linear_kernel(const DecodeLinear a) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   __shared__ float red[4][DL_ROWS][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane & 3, g = lane >> 2;
@@ -518,6 +530,8 @@ argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restri
                        float* __restrict__ margin_out, int* __restrict__ out_tokens, float* __restrict__ out_margin,
                        int* __restrict__ out_len, int* __restrict__ done, int max_new, const int* __restrict__ step_p,
                        int eot) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   __shared__ Top2 sh[8];
   const int s = blockIdx.x;
   const float* p = part + (size_t)s * n_part * 3;
@@ -554,6 +568,8 @@ argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restri
 }
 
 __global__ void advance_kernel(int* n_past, int add, int* step) {
+  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
+  pdl_launch_dependents();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *n_past += add;
     if (step) *step += 1;
@@ -564,15 +580,14 @@ __global__ void advance_kernel(int* n_past, int add, int* step) {
 
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
                          const int* n_past_dev, int d, float* x, cudaStream_t st) {
-  embed_kernel<<<n_seq * n_tok, 128, 0, st>>>(te, pe, tokens, n_tok, n_past_dev, d, x);
-  return cudaGetLastError();
+  return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x);
 }
 
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
                                     const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st) {
   if (n_text_ctx > SELF_MAX_CTX) return cudaErrorInvalidValue;
-  decode_self_attn_kernel<<<dim3(H, n_seq), SELF_THREADS, 0, st>>>(qkv, d, kc, vc, n_tok, n_past_dev, n_text_ctx, out);
-  return cudaGetLastError();
+  return launch_pdl(decode_self_attn_kernel, dim3(H, n_seq), dim3(SELF_THREADS), 0, st, qkv, d, kc, vc, n_tok, n_past_dev,
+                    n_text_ctx, out);
 }
 
 int decode_cross_splits(int n_seq, int H, int T, int num_sms) {
@@ -586,12 +601,10 @@ cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, co
                                      int n_split, cudaStream_t st) {
   const int span = (T + n_split - 1) / n_split;
   if (span > CROSS_MAX_SPAN) return cudaErrorInvalidValue;
-  decode_cross_attn_kernel<<<dim3(H, n_seq, n_split), CROSS_THREADS, 0, st>>>(q, d, k, v, ld_kv, n_tok, T, span, out,
-                                                                             part_o, part_ml, n_split);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(decode_cross_attn_kernel, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
+                             n_tok, T, span, out, part_o, part_ml, n_split);
   if (e != cudaSuccess || n_split == 1) return e;
-  cross_combine_kernel<<<dim3(H, n_seq * n_tok), DH, 0, st>>>(part_o, part_ml, n_split, d, out);
-  return cudaGetLastError();
+  return launch_pdl(cross_combine_kernel, dim3(H, n_seq * n_tok), dim3(DH), 0, st, part_o, part_ml, n_split, d, out);
 }
 
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
@@ -604,22 +617,19 @@ cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next
 
 cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st) {
   if (a.R < 1 || a.R > 32 || a.N < 1 || a.K % 64 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
-  decode_linear_kernel<<<(a.N + DL_ROWS - 1) / DL_ROWS, DL_THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(decode_linear_kernel, dim3((a.N + DL_ROWS - 1) / DL_ROWS), dim3(DL_THREADS), 0, st, a);
 }
 int decode_linear_parts(int N) { return (N + DL_ROWS - 1) / DL_ROWS; }
 
 cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
                                    int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
                                    const int* step_dev, int eot, cudaStream_t st) {
-  argmax_partials_kernel<<<n_seq, 256, 0, st>>>(part, n_part, next_tok, margin, out_tokens, out_margin, out_len, done,
-                                                max_new, step_dev, eot);
-  return cudaGetLastError();
+  return launch_pdl(argmax_partials_kernel, dim3(n_seq), dim3(256), 0, st, part, n_part, next_tok, margin, out_tokens,
+                    out_margin, out_len, done, max_new, step_dev, eot);
 }
 
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st) {
-  advance_kernel<<<1, 32, 0, st>>>(n_past_dev, add, step_dev);
-  return cudaGetLastError();
+  return launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, n_past_dev, add, step_dev);
 }
 
 }  // namespace wb

@@ -173,7 +173,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
     const DecLayer& l = ctx->dec[il];
     {   // D2: self-attention
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.attn_ln_w, l.attn_ln_b, R, d, ctx->d_ln, nullptr, st));
+      WB_CK(launch_layernorm(ctx->dx, l.attn_ln_w, l.attn_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
@@ -199,7 +199,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
     }
     {   // D3: cross-attention over memory_cross_k/v written by wb_encode
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.cross_ln_w, l.cross_ln_b, R, d, ctx->d_ln, nullptr, st));
+      WB_CK(launch_layernorm(ctx->dx, l.cross_ln_w, l.cross_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
@@ -225,7 +225,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
     }
     {   // D4: MLP
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.mlp_ln_w, l.mlp_ln_b, R, d, ctx->d_ln, nullptr, st));
+      WB_CK(launch_layernorm(ctx->dx, l.mlp_ln_w, l.mlp_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
@@ -248,7 +248,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
   {   // D5: logits of the last position of every sequence
     LaunchTimer t(ctx, "dec_layernorm");
     WB_CK(launch_layernorm(ctx->dx + (size_t)(n_tok - 1) * d, ctx->d_ln_w, ctx->d_ln_b, n_seq, d, ctx->d_lnf, nullptr,
-                           st, (long long)n_tok * d));
+                           st, (long long)n_tok * d, true));
   }
   {
     GemmEpilogue e;
