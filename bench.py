@@ -278,7 +278,12 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
     if rank == 0:
         sampler.start()   # early, so nvidia-smi is already streaming when the timed regions begin
     model = ensure_model(pkg, arch, rank, barrier)
-    stream = torch.cuda.current_stream()
+    # the context runs on this stream, and the timed regions are bracketed by events recorded on it (torch's
+    # default stream has handle 0, which the C-ABI reads as "create your own": events recorded on the default
+    # stream would not see the library's kernels)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples, device=local_rank,
                                  stream=stream.cuda_stream, decode_capacity=False)
     # ---- synthetic inputs: N_ROT distinct batches so no step re-reads the previous step's PCM
@@ -295,34 +300,46 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
         api.whisper_pcm_to_mel(ctx, devb[i % n_rot])
         api.whisper_encode(ctx, 1, offs, clip_ids=ids)
 
-    # ---- end-to-end leg: two contexts (each its own stream, staging buffers and activations) take
-    # alternate steps, so one step's host-side launches, H2D upload and D2H read-back overlap the other
-    # step's kernels -- the way a throughput server drives the library
-    ctx_b = api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples, device=local_rank,
-                                   decode_capacity=False)
+    # ---- end-to-end leg through the host-facing calls on HOST buffers.  One context, software-pipelined one
+    # step deep: step i+1's upload runs on the context's copy stream (wb_pcm_prefetch) under step i's encoder,
+    # and step i+1 is submitted before step i's result is awaited (wb_encoder_digest_async / wb_wait), so the
+    # stream never drains.  (--e2e-mode dual: the earlier scheme, two contexts on two streams in alternation.)
+    n_e2e_ctx = 2 if args.e2e_mode == "dual" else 1
     e2e_ctx = [api.WhisperContext.new(model, max_segments=B, max_clips=B, max_clip_samples=n_samples,
-                                      device=local_rank, decode_capacity=False), ctx_b]
+                                      device=local_rank, decode_capacity=False) for _ in range(n_e2e_ctx)]
+    res = torch.zeros(8, B, dtype=torch.float64).pin_memory()
+    pcm_bytes = B * n_samples * 4
 
-    def e2e_submit(i):
-        cx, h = e2e_ctx[i % 2], host[i % n_rot]
-        api.whisper_pcm_to_mel_ptr(cx, h.data_ptr(), n_samples, B)   # H2D from pinned host memory (this step's input)
+    def e2e_submit(i, k):
+        cx, h = e2e_ctx[i % n_e2e_ctx], host[i % n_rot]
+        # H2D of this step's input from pinned host memory: already in flight on the copy stream when it was
+        # prefetched during the previous step (single), else copied here on the compute stream
+        api.whisper_pcm_to_mel_ptr(cx, h.data_ptr(), n_samples, B)
+        if n_e2e_ctx == 1 and i + 1 < k:
+            api.whisper_pcm_prefetch_ptr(cx, host[(i + 1) % n_rot].data_ptr(), pcm_bytes)
         api.whisper_encode(cx, 1, offs, clip_ids=ids)
-
-    def e2e_collect(i):
-        return e2e_ctx[i % 2].encoder_digest(B)                      # D2H read of this step's result (syncs its stream)
+        return api.encoder_digest_async(cx, res[i % 8].data_ptr(), B)   # D2H of this step's result, queued
 
     def run_e2e(k):
-        """k steps, software-pipelined one deep: step i+1 is submitted before step i's result is read."""
+        """k steps; step i+1 is submitted before step i's result is awaited."""
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_submit(0)
+        if n_e2e_ctx == 1:
+            api.whisper_pcm_prefetch_ptr(e2e_ctx[0], host[0].data_ptr(), pcm_bytes)
+        tickets = [e2e_submit(0, k)]
+        trace = []
         for i in range(k):
+            ta = time.perf_counter()
             if i + 1 < k:
-                e2e_submit(i + 1)
-            e2e_collect(i)
+                tickets.append(e2e_submit(i + 1, k))
+            tb = time.perf_counter()
+            api.wait(e2e_ctx[i % n_e2e_ctx], tickets[i])
+            trace.append((round((tb - ta) * 1e3, 3), round((time.perf_counter() - tb) * 1e3, 3)))
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
+        if os.environ.get("WB_BENCH_DEBUG"):
+            log(f"[e2e] k={k} total {ms:.2f} ms; per step (host submit ms, wait ms): {trace}")
         barrier()
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -414,11 +431,14 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
                 "sharding": "independent segments per rank, no data-path collective; one all_gather of digests",
                 "cache": f"per-step working set (~{(B * 1500 * hp.n_audio_state * 2 * (8 + 4 * hp.n_text_layer)) / 1e6:.0f} MB of "
                          f"activations) exceeds the 126 MB L2; PCM rotates over {n_rot} distinct batches",
-                "e2e_pipeline": "each e2e step = whisper_pcm_to_mel(pinned host PCM, H2D inside) + whisper_encode + "
-                                "encoder_digest read-back (D2H, syncs that context's stream); two contexts on their own "
-                                "streams take alternate steps and step i+1 is submitted before step i's result is read, "
-                                "so uploads, launches and read-backs overlap the other step's kernels; timed with the "
-                                "host clock between device-wide synchronisations (two streams), max over ranks",
+                "e2e_pipeline": ("each e2e step = H2D of the step's pinned host PCM (wb_pcm_prefetch on the context's "
+                                 "copy stream, issued one step ahead) + whisper_pcm_to_mel + whisper_encode + digest "
+                                 "read-back (D2H, wb_encoder_digest_async); step i+1 is submitted before step i's "
+                                 "result is awaited; one context, one compute stream" if n_e2e_ctx == 1 else
+                                 "each e2e step = whisper_pcm_to_mel(pinned host PCM, H2D inside) + whisper_encode + "
+                                 "digest read-back (D2H); two contexts on their own streams take alternate steps and "
+                                 "step i+1 is submitted before step i's result is awaited") +
+                                "; timed with the host clock between device-wide synchronisations, max over ranks",
                 "roofline_timing": "third timed pass of the same K steps with per-launch CUDA events on the launching stream",
             },
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * n_samples * 4,
@@ -472,6 +492,7 @@ def main():
     ap.add_argument("--cpu-segments", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decoder", action="store_true", help="skip the decoder tokens/sec leg")
+    ap.add_argument("--e2e-mode", default="dual", choices=["single", "dual"])
     ap.add_argument("--dec-arch", default="small")
     ap.add_argument("--dec-batch", type=int, default=32)
     ap.add_argument("--dec-tokens", type=int, default=224)

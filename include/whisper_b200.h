@@ -47,7 +47,9 @@ typedef struct wb_config {
   int32_t max_segments;    /* encoder/decoder batch capacity (30 s windows per wb_encode call) */
   int32_t max_clips;       /* clips per wb_pcm_to_mel call */
   int64_t max_clip_samples;/* longest clip, in samples */
-  int32_t norm_scope;      /* WB_NORM_CLIP = whole-clip max as clamp_and_normalize (1654-1671) */
+  int32_t norm_scope;      /* WB_NORM_CLIP = whole-clip max as clamp_and_normalize (1654-1671); the only scope
+                              implemented (wb_ctx_create rejects others).  A clip split across GPUs keeps the
+                              whole-clip maximum through wb_pcm_to_logmel / wb_mel_normalize */
   int32_t checkpoints;     /* 1: keep sum|x| probes per stage (the author's debug probes, 1836-1849) */
   void*   stream;          /* cudaStream_t to run on; NULL = the library creates its own */
   int32_t decode_capacity; /* 1: allocate self-attention KV for max_segments sequences */
@@ -91,6 +93,19 @@ int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_cli
  * instead of copying again.  The caller keeps the host buffer unchanged until that call.  (The
  * reference holds its samples in an Arc<Vec<f32>> shared with its mel threads, 1584, 1681.) */
 int wb_pcm_prefetch(wb_ctx* ctx, const void* pcm, size_t n_bytes);
+/* whisper_pcm_to_mel in two phases, for ONE long clip whose samples are split across GPUs (each
+ * GPU holds the span of its own 30 s windows plus the 240-sample halo frame i = [160i, 160i+400)
+ * reaches into, 1594-1597).  The whole-clip maximum of clamp_and_normalize (1655-1662) is the only
+ * coupling between the parts:
+ *   wb_pcm_to_logmel   log10 mel (1554-1652) of exactly n_frames frames per clip (0 = n_samples/160;
+ *                      samples past n_samples read as zero, 1596-1600) + the local per-clip maximum
+ *   wb_mel_max_read    that maximum -> the caller takes the MAX over all parts (one 4-byte all-reduce)
+ *   wb_mel_normalize   x = max(x, max - 8); x = (x + 4) / 4 (1664-1670) with the combined maxima
+ *                      (clip_max NULL = the local ones, which makes the two calls equal wb_pcm_to_mel)
+ * wb_encode refuses a mel that has not been normalised. */
+int wb_pcm_to_logmel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips, int n_frames);
+int wb_mel_max_read(wb_ctx* ctx, float* out, int n_clips);
+int wb_mel_normalize(wb_ctx* ctx, const float* clip_max, int n_clips);
 int wb_mel_dims(const wb_ctx* ctx, int* n_mel, int* n_len, int* n_clips);
 int wb_mel_read(wb_ctx* ctx, int clip, float* out, size_t cap_floats);   /* [n_mel][n_len], layout of 1633 */
 int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clips); /* set ctx.mel directly */
@@ -106,6 +121,12 @@ int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum);
 /* sum|x| of every encoded segment's ln_post output in one call (the author's probe, 1836-1849, applied
  * to `cur` after 1984): out[n_segments] doubles.  The small host-visible result of an encode step. */
 int wb_encoder_digest(wb_ctx* ctx, double* out, int cap);
+/* Non-blocking form: the digest and its read-back into `out` (pinned host memory) are queued on the
+ * handle's stream; returns a ticket (>= 0) for wb_wait.  Lets a caller submit batch i+1 (mel + encode)
+ * before it waits for batch i's result, so one handle keeps its stream full.  Up to 8 tickets may be
+ * outstanding. */
+int wb_encoder_digest_async(wb_ctx* ctx, double* out, int cap);
+int wb_wait(wb_ctx* ctx, int ticket);
 
 /* The decode step the reference declares state for but never implements (694-731, 1336-1354,
  * logits/probs 351-352): tokens is HOST [n_seqs][n_tokens]; sequence i attends to the cross K/V

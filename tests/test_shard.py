@@ -25,6 +25,31 @@ def test_segments_for_rank(pkg):
     assert hi == 120 * 480000
 
 
+def test_clip_parts_cover_the_clip(pkg):
+    """One long clip over G ranks: every window once, every frame once, and every sample a rank's frames read
+    lies inside its span or past the end of the clip (where the reference zero-fills, src/main.rs:1596-1600)."""
+    import importlib
+    pipeline = importlib.import_module("whisper_rs_b200.pipeline")
+    for fpw in (3000, 192):
+        for n in (100, 160 * fpw - 1, 160 * fpw, 160 * fpw + 1, int(2.6 * 160 * fpw) + 77, 7 * 160 * fpw, 120 * 160 * fpw):
+            n_len = n // 160
+            for G in (1, 2, 3, 8):
+                parts = [pipeline.ClipPart(n, r, G, fpw) for r in range(G)]
+                wins = sorted(w for p in parts for w in p.windows)
+                assert wins == list(range(pipeline.n_windows(n, fpw)))
+                assert sum(p.n_frames for p in parts) == n_len
+                for p in parts:
+                    if not p.windows or p.n_frames == 0:
+                        continue
+                    f0 = p.windows[0] * fpw
+                    assert p.lo == 160 * f0 and p.local_offset(p.windows[-1]) == (len(p.windows) - 1) * fpw
+                    last = 160 * (f0 + p.n_frames - 1) + 400      # one past the last sample the part's frames read
+                    assert p.hi >= min(last, n) and p.hi <= n
+    # config 5: 1 h of audio = 120 windows over 8 GPUs, 15 each
+    parts = [pipeline.ClipPart(3600 * 16000, r, 8) for r in range(8)]
+    assert [len(p.windows) for p in parts] == [15] * 8 and parts[1].hi - parts[1].lo == 15 * 480000 + 240
+
+
 WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np
@@ -44,6 +69,12 @@ WORKER = textwrap.dedent("""
         assert (full == want).all(), (rank, contiguous, full)
         dig = pkg.shard.gather_segment_results(np.array([float(s) + 0.5 for s in segs]), segs, S)
         assert np.allclose(dig, np.arange(S) + 0.5)
+    # the one coupling of a split clip: the whole-clip maximum (clamp_and_normalize, src/main.rs:1655-1662)
+    import importlib
+    pipeline = importlib.import_module("whisper_rs_b200.pipeline")
+    local = [3.25, -1.5][rank]
+    assert pipeline.torch_reduce_max()(local) == 3.25
+    assert pipeline.torch_reduce_max()(-1e20 if rank == 0 else -7.0) == -7.0     # a rank with no frames
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")

@@ -199,6 +199,44 @@ def whisper_pcm_prefetch_ptr(ctx: WhisperContext, host_ptr: int, n_bytes: int) -
     _check(cabi.lib().wb_pcm_prefetch(ctx._h, host_ptr, n_bytes), ctx._h)
 
 
+def whisper_pcm_to_logmel(ctx: WhisperContext, samples, n_frames: int = 0) -> np.ndarray:
+    """Phase 1 of whisper_pcm_to_mel for a clip split across GPUs: log10 mel (src/main.rs:1554-1652) of
+    exactly `n_frames` frames (0 = n_samples / 160) of this part of the clip; returns the local per-clip
+    maxima (the partial result of the scan at 1655-1662)."""
+    a = np.ascontiguousarray(np.asarray(samples), dtype=np.float32)
+    n_clips = 1 if a.ndim == 1 else a.shape[0]
+    L = cabi.lib()
+    _check(L.wb_pcm_to_logmel(ctx._h, a.ctypes.data, a.shape[-1], n_clips, n_frames), ctx._h)
+    mx = np.zeros(n_clips, dtype=np.float32)
+    _check(L.wb_mel_max_read(ctx._h, _f32p(mx), n_clips), ctx._h)
+    return mx
+
+
+def whisper_mel_normalize(ctx: WhisperContext, clip_max=None) -> None:
+    """Phase 2: clamp_and_normalize (src/main.rs:1654-1671) with the whole-clip maxima `clip_max`
+    (MAX over every part of the clip); None = this part's own maxima."""
+    L = cabi.lib()
+    if clip_max is None:
+        n = C.c_int()
+        L.wb_mel_dims(ctx._h, None, None, C.byref(n))
+        _check(L.wb_mel_normalize(ctx._h, None, n.value), ctx._h)
+        return
+    mx = np.ascontiguousarray(np.atleast_1d(np.asarray(clip_max, dtype=np.float32)))
+    _check(L.wb_mel_normalize(ctx._h, _f32p(mx), mx.size), ctx._h)
+
+
+def encoder_digest_async(ctx: WhisperContext, out_ptr: int, cap: int) -> int:
+    """Queue the per-segment digest and its read-back into pinned host memory at `out_ptr` behind the last
+    whisper_encode; returns a ticket for `wait` (the caller may submit the next batch first)."""
+    t = cabi.lib().wb_encoder_digest_async(ctx._h, out_ptr, cap)
+    _check(min(t, 0), ctx._h)
+    return t
+
+
+def wait(ctx: WhisperContext, ticket: int) -> None:
+    _check(cabi.lib().wb_wait(ctx._h, ticket), ctx._h)
+
+
 def whisper_encode(ctx: WhisperContext, n_threads: int = 1, mel_offset=0,
                    clip_ids: Optional[Sequence[int]] = None) -> None:
     """src/main.rs:1799.  `n_threads` is accepted and ignored, as in the reference (1799, 2074).

@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
     L.wb_pcm_to_mel_device.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
     L.wb_pcm16_to_mel.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
     L.wb_pcm_prefetch.argtypes = [vp, C.c_void_p, C.c_size_t]
+    L.wb_pcm_to_logmel.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    L.wb_mel_max_read.argtypes = [vp, f32p, C.c_int]
+    L.wb_mel_normalize.argtypes = [vp, f32p, C.c_int]
     L.wb_token_text.argtypes = [vp, C.c_int32, C.c_char_p, C.c_size_t]
     L.wb_tokens_to_text.argtypes = [vp, C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.c_size_t]
     L.wb_mel_dims.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -84,6 +87,8 @@ def lib() -> C.CDLL:
     L.wb_cross_kv_read.argtypes = [vp, C.c_int, C.c_int, u16p, u16p]
     L.wb_checksum.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.wb_encoder_digest.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    L.wb_encoder_digest_async.argtypes = [vp, C.c_void_p, C.c_int]
+    L.wb_wait.argtypes = [vp, C.c_int]
     L.wb_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int]
     L.wb_logits_read.argtypes = [vp, C.c_int, f32p]
     L.wb_decode_greedy.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, f32p, i32p]

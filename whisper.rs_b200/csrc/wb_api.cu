@@ -441,6 +441,12 @@ int alloc_activations(wb_ctx* ctx) {
     WB_CK(cudaEventCreateWithFlags(&ctx->ev_mel_read[i], cudaEventDisableTiming));
   }
   ctx->d_pcm = ctx->d_pcm_buf[0];
+  for (int i = 0; i < WB_N_TICKETS; ++i) {
+    WB_CK(cudaEventCreateWithFlags(&ctx->ev_ticket[i], cudaEventDisableTiming));
+    WB_CK(cudaEventCreateWithFlags(&ctx->ev_seg_slot[i], cudaEventDisableTiming));
+  }
+  WB_CK(cudaHostAlloc((void**)&ctx->h_clip_ids, sizeof(int) * WB_N_TICKETS * ctx->cfg.max_segments, cudaHostAllocDefault));
+  WB_CK(cudaHostAlloc((void**)&ctx->h_offsets, sizeof(long long) * WB_N_TICKETS * ctx->cfg.max_segments, cudaHostAllocDefault));
   WB_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if ((rc = dev_alloc(ctx, &ctx->d_clip_max, (size_t)ctx->cfg.max_clips))) return rc;
   return WB_OK;
@@ -503,6 +509,8 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: n_audio_state != n_text_state");
   if (hp.n_audio_state % 64 != 0 || hp.n_audio_state > 1280 || hp.n_mels % 8 != 0 || mv.filt_n_mel != hp.n_mels)
     return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: unsupported model dimensions");
+  if (cfg.norm_scope != WB_NORM_CLIP)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: only the whole-clip normalisation scope of the reference is implemented");
 
   // ---- device: no CPU fallback
   int n_dev = 0;
@@ -620,6 +628,12 @@ void wb_ctx_free(wb_ctx* ctx) {
     if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
     if (ctx->ev_mel_read[i]) cudaEventDestroy(ctx->ev_mel_read[i]);
   }
+  for (int i = 0; i < WB_N_TICKETS; ++i) {
+    if (ctx->ev_ticket[i]) cudaEventDestroy(ctx->ev_ticket[i]);
+    if (ctx->ev_seg_slot[i]) cudaEventDestroy(ctx->ev_seg_slot[i]);
+  }
+  if (ctx->h_clip_ids) cudaFreeHost(ctx->h_clip_ids);
+  if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -672,9 +686,9 @@ int wb_sync(wb_ctx* ctx) {
 
 // ------------------------------------------------------------------------------------------------
 // whisper_pcm_to_mel (src/main.rs:1681-1707)
-static int mel_run(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_samples, int n_clips) {
+// stage 1: log10-mel of n_len frames per clip + the per-clip maximum (1554-1652, 1655-1662)
+static int mel_logmel(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_samples, int n_clips, size_t n_len) {
   const int n_mel = ctx->mel_tab.n_mel;
-  const size_t n_len = n_samples / 160;   // 1575
   if (n_clips < 1 || n_clips > ctx->cfg.max_clips || (size_t)n_clips * n_mel * n_len > ctx->d_mel_floats)
     return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
   cudaEventRecord(ctx->ev[0][0], ctx->stream);
@@ -687,12 +701,21 @@ static int mel_run(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_sample
     WB_CK(launch_mel_frames(ctx->mel_tab, pcm_dev, is_i16, n_samples, n_clips, (int)n_len, ctx->d_mel, ctx->d_clip_max,
                             ctx->stream));
   }
+  ctx->mel_n_len = (int)n_len;
+  ctx->mel_n_clips = n_clips;
+  ctx->mel_normalized = false;
+  return WB_OK;
+}
+
+// stage 2: clamp_and_normalize (1654-1671) with the maxima in d_clip_max
+static int mel_norm(wb_ctx* ctx) {
+  const int n_mel = ctx->mel_tab.n_mel, n_clips = ctx->mel_n_clips;
+  const size_t n_len = (size_t)ctx->mel_n_len;
   {
     LaunchTimer t(ctx, "mel_normalize");
     WB_CK(launch_mel_normalize(ctx->d_mel, n_clips, (size_t)n_mel * n_len, ctx->d_clip_max, ctx->stream));
   }
-  ctx->mel_n_len = (int)n_len;
-  ctx->mel_n_clips = n_clips;
+  ctx->mel_normalized = true;
   if (ctx->cfg.checkpoints) {
     WB_CK(launch_abs_sum_f32(ctx->d_mel, (long long)n_mel * n_len, (long long)n_mel * n_len,
                              n_clips < ctx->cfg.max_segments ? n_clips : ctx->cfg.max_segments, ctx->d_chk, ctx->stream));
@@ -702,6 +725,11 @@ static int mel_run(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_sample
   ctx->ev_used[0] = true;
   ctx->tm.n_mel_calls += 1;
   return WB_OK;
+}
+
+static int mel_run(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_samples, int n_clips) {
+  int rc = mel_logmel(ctx, pcm_dev, is_i16, n_samples, n_clips, n_samples / 160);   // n_len, 1575
+  return rc ? rc : mel_norm(ctx);
 }
 
 int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, int n_clips) {
@@ -747,6 +775,41 @@ int wb_pcm16_to_mel(wb_ctx* ctx, const int16_t* pcm, size_t n_samples, int n_cli
   return rc;
 }
 
+// Two-phase whisper_pcm_to_mel for a clip whose samples are split across GPUs: the
+// whole-clip maximum of clamp_and_normalize (1655-1662) is the one coupling between the parts.
+int wb_pcm_to_logmel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips, int n_frames) {
+  if (!ctx || !pcm || n_clips < 1 || n_frames < 0) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  int rc = stage_host_pcm(ctx, pcm, (size_t)n_clips * n_samples * 4);
+  if (rc) return rc;
+  rc = mel_logmel(ctx, ctx->d_pcm, 0, n_samples, n_clips, n_frames ? (size_t)n_frames : n_samples / 160);
+  if (rc == WB_OK) WB_CK(cudaEventRecord(ctx->ev_mel_read[ctx->pcm_cur], ctx->stream));
+  return rc;
+}
+
+int wb_mel_max_read(wb_ctx* ctx, float* out, int n_clips) {
+  if (!ctx || !out || n_clips < 1 || n_clips > ctx->mel_n_clips) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  std::vector<int> enc((size_t)n_clips);
+  WB_CK(cudaMemcpyAsync(enc.data(), ctx->d_clip_max, sizeof(int) * n_clips, cudaMemcpyDeviceToHost, ctx->stream));
+  WB_CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_clips; ++i) out[i] = mel_dec_ordered_host(enc[(size_t)i]);
+  return WB_OK;
+}
+
+int wb_mel_normalize(wb_ctx* ctx, const float* clip_max, int n_clips) {
+  if (!ctx || n_clips != ctx->mel_n_clips || ctx->mel_n_clips < 1) return WB_ERR_UNEXPECTED;
+  if (ctx->mel_normalized) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected error: mel is already normalised\n");
+  cudaSetDevice(ctx->device);
+  if (clip_max) {
+    std::vector<int> enc((size_t)n_clips);
+    for (int i = 0; i < n_clips; ++i) enc[(size_t)i] = mel_enc_ordered_host(clip_max[i]);
+    WB_CK(cudaMemcpyAsync(ctx->d_clip_max, enc.data(), sizeof(int) * n_clips, cudaMemcpyHostToDevice, ctx->stream));
+    WB_CK(cudaStreamSynchronize(ctx->stream));   // enc is a stack-lifetime host buffer
+  }
+  return mel_norm(ctx);
+}
+
 int wb_pcm_prefetch(wb_ctx* ctx, const void* pcm, size_t n_bytes) {
   if (!ctx || !pcm) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
@@ -789,6 +852,7 @@ int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clip
   WB_CK(cudaStreamSynchronize(ctx->stream));
   ctx->mel_n_len = n_len;
   ctx->mel_n_clips = n_clips;
+  ctx->mel_normalized = true;
   return WB_OK;
 }
 
@@ -802,6 +866,8 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
   if (ctx->mel_n_clips < 1 || ctx->mel_tab.n_mel != hp.n_mels)   // assert 1813
     return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: no mel in the context (call wb_pcm_to_mel first)");
+  if (!ctx->mel_normalized)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: the mel is not normalised (call wb_mel_normalize after wb_pcm_to_logmel)");
   const int T = hp.n_audio_ctx, Tm = 2 * T, d = hp.n_audio_state, H = hp.n_audio_head, L = hp.n_audio_layer;
   const int Lt = hp.n_text_layer, n_mels = hp.n_mels;
   const int M = n_seg * T;
@@ -809,18 +875,22 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   cudaStream_t st = ctx->stream;
   const char* terr = "";
 
-  // segment table
-  std::vector<int> ids(n_seg, 0);
-  std::vector<long long> offs(n_seg, 0);
+  // segment table: through a ring of pinned host slots, so the call never waits for the stream (a caller may
+  // queue the next batch while this one runs); a slot is reused only after the copy that read it has executed
+  const int slot = ctx->seg_slot_next;
+  ctx->seg_slot_next = (slot + 1) % WB_N_TICKETS;
+  WB_CK(cudaEventSynchronize(ctx->ev_seg_slot[slot]));
+  int* ids = ctx->h_clip_ids + (size_t)slot * ctx->cfg.max_segments;
+  long long* offs = ctx->h_offsets + (size_t)slot * ctx->cfg.max_segments;
   for (int s = 0; s < n_seg; ++s) {
-    if (clip_ids) ids[s] = clip_ids[s];
-    if (mel_offsets) offs[s] = (long long)mel_offsets[s];
+    ids[s] = clip_ids ? clip_ids[s] : 0;
+    offs[s] = mel_offsets ? (long long)mel_offsets[s] : 0;
     if (ids[s] < 0 || ids[s] >= ctx->mel_n_clips) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: clip id out of range");
   }
   cudaEventRecord(ctx->ev[1][0], st);
-  WB_CK(cudaMemcpyAsync(ctx->d_clip_ids, ids.data(), sizeof(int) * n_seg, cudaMemcpyHostToDevice, st));
-  WB_CK(cudaMemcpyAsync(ctx->d_offsets, offs.data(), sizeof(long long) * n_seg, cudaMemcpyHostToDevice, st));
-  WB_CK(cudaStreamSynchronize(st));   // ids/offs are stack temporaries (tiny copy)
+  WB_CK(cudaMemcpyAsync(ctx->d_clip_ids, ids, sizeof(int) * n_seg, cudaMemcpyHostToDevice, st));
+  WB_CK(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(long long) * n_seg, cudaMemcpyHostToDevice, st));
+  WB_CK(cudaEventRecord(ctx->ev_seg_slot[slot], st));
 
   // ---- tensor maps of the activation operands for this batch size
   CUtensorMap m_conv1, m_conv2, m_ln, m_att, m_hid, m_enc;
@@ -1029,6 +1099,31 @@ int wb_encoder_digest(wb_ctx* ctx, double* out, int cap) {
   }
   WB_CK(cudaMemcpyAsync(out, slot, sizeof(double) * ctx->enc_n_seg, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
+  return WB_OK;
+}
+
+// The same digest without blocking: the read-back is queued on the handle's stream behind the encode
+// that produced it, so the caller can submit the next batch before it waits for this one.
+int wb_encoder_digest_async(wb_ctx* ctx, double* out, int cap) {
+  if (!ctx || !out || ctx->enc_n_seg < 1 || cap < ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  const long long n = (long long)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
+  {
+    LaunchTimer t(ctx, "digest");
+    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->stream));
+  }
+  WB_CK(cudaMemcpyAsync(out, slot, sizeof(double) * ctx->enc_n_seg, cudaMemcpyDeviceToHost, ctx->stream));
+  const int ticket = ctx->ticket_next;
+  ctx->ticket_next = (ticket + 1) % WB_N_TICKETS;
+  WB_CK(cudaEventRecord(ctx->ev_ticket[ticket], ctx->stream));
+  return ticket;
+}
+
+int wb_wait(wb_ctx* ctx, int ticket) {
+  if (!ctx || ticket < 0 || ticket >= WB_N_TICKETS) return WB_ERR_UNEXPECTED;
+  cudaSetDevice(ctx->device);
+  WB_CK(cudaEventSynchronize(ctx->ev_ticket[ticket]));
   return WB_OK;
 }
 

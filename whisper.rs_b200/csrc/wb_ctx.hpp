@@ -45,6 +45,8 @@ struct KernelClock {   // device time per kernel family (CUDA events on the hand
 
 }  // namespace wb
 
+constexpr int WB_N_TICKETS = 8;
+
 struct wb_ctx {
   wb_config cfg{};
   int device = 0;
@@ -85,10 +87,15 @@ struct wb_ctx {
   size_t d_mel_floats = 0;
   int* d_clip_max = nullptr;
   int mel_n_len = 0, mel_n_clips = 0;
+  bool mel_normalized = false;        // false between wb_pcm_to_logmel and wb_mel_normalize
 
   // ---- encoder activations (capacity = cfg.max_segments)
   int* d_clip_ids = nullptr;
   long long* d_offsets = nullptr;
+  int* h_clip_ids = nullptr;          // pinned ring [WB_N_TICKETS][max_segments] the segment table is uploaded from
+  long long* h_offsets = nullptr;
+  cudaEvent_t ev_seg_slot[WB_N_TICKETS] = {};
+  int seg_slot_next = 0;
   __half* conv_in = nullptr;          // [seg][Tm+2][n_mel]
   __half* h1 = nullptr;               // [seg][Tm+2][d]
   float* x = nullptr;                 // residual stream [seg*T][d] f32
@@ -124,6 +131,10 @@ struct wb_ctx {
   int dec_n_seq = 0;
   cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
   int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;
+
+  // ---- results read back without blocking (wb_encoder_digest_async / wb_wait)
+  cudaEvent_t ev_ticket[WB_N_TICKETS] = {};
+  int ticket_next = 0;
 
   // ---- timing
   cudaEvent_t ev[3][2] = {};          // [mel|encode|decode][start|stop] of the most recent call
