@@ -12,8 +12,10 @@ template <int OP>
 __global__ void k(float* out, long long* cyc, float seed) {
   float a[ILP];
   uint32_t h[ILP];
+  unsigned long long d[ILP];
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) { a[i] = seed + threadIdx.x * 0.001f + i; h[i] = 0x3c003800u + threadIdx.x + i; }
+  for (int i = 0; i < ILP; ++i) { a[i] = seed + threadIdx.x * 0.001f + i; h[i] = 0x3c003800u + threadIdx.x + i;
+    d[i] = ((unsigned long long)__float_as_uint(a[i]) << 32) | __float_as_uint(a[i] * 0.5f); }
   __syncthreads();
   long long t0 = clock64();
 #pragma unroll 1
@@ -32,12 +34,15 @@ __global__ void k(float* out, long long* cyc, float seed) {
       if (OP == 9) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
       if (OP == 10) { int x = __float_as_int(a[i]); asm volatile("shl.b32 %0, %0, 23;" : "+r"(x)); a[i] = __int_as_float(x); }
       if (OP == 11) asm volatile("cvt.rn.f16.f32 %0, %1;" : "=h"(*(unsigned short*)&h[i]) : "f"(a[i]));
+      if (OP == 12) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(d[i]) : "l"(d[(i + 1) % ILP]));   // 2 FMAs per thread-instr
+      if (OP == 13) asm volatile("add.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(d[(i + 1) % ILP]));
+      if (OP == 14) asm volatile("mul.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(d[(i + 1) % ILP]));
     }
   }
   long long t1 = clock64();
   float s = 0; uint32_t x = 0;
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) { s += a[i]; x ^= h[i]; }
+  for (int i = 0; i < ILP; ++i) { s += a[i]; x ^= h[i]; x ^= (uint32_t)(d[i] >> 32) ^ (uint32_t)d[i]; }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)x;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -58,6 +63,7 @@ void run(const char* name, int warps) {
 
 int main() {
   for (int w : {4, 8, 16}) {
+    run<12>("fma.f32x2", w); run<13>("add.f32x2", w); run<14>("mul.f32x2", w);
     if (w == 4) { run<0>("ex2.approx.ftz.f32", 4); run<1>("ex2.approx.f16x2", 4); run<7>("ex2.approx.ftz.bf16x2", 4); run<2>("cvt.rn.f16x2.f32", 4); run<11>("cvt.rn.f16.f32", 4); run<3>("fma.f32", 4); run<4>("max.f32", 4); run<5>("max3.f32", 4); run<6>("fma.f16x2", 4); run<8>("tanh.approx.f32", 4); run<9>("add.f32", 4); run<10>("shl.b32", 4); }
     if (w == 8) { run<0>("ex2.approx.ftz.f32", 8); run<1>("ex2.approx.f16x2", 8); run<7>("ex2.approx.ftz.bf16x2", 8); run<2>("cvt.rn.f16x2.f32", 8); run<11>("cvt.rn.f16.f32", 8); run<3>("fma.f32", 8); run<4>("max.f32", 8); run<5>("max3.f32", 8); run<6>("fma.f16x2", 8); run<8>("tanh.approx.f32", 8); run<9>("add.f32", 8); run<10>("shl.b32", 8); }
     if (w == 16) { run<0>("ex2.approx.ftz.f32", 16); run<1>("ex2.approx.f16x2", 16); run<2>("cvt.rn.f16x2.f32", 16); run<3>("fma.f32", 16); run<4>("max.f32", 16); run<5>("max3.f32", 16); }

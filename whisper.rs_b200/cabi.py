@@ -14,7 +14,8 @@ from typing import List, Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libwhisper_b200.so")
+# WB_LIB: an alternative build of the same library (A/B runs of kernel variants on the GPU box)
+LIB_PATH = os.environ.get("WB_LIB") or os.path.join(CSRC, "libwhisper_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "whisper_b200.h")
 _lib: Optional[C.CDLL] = None
 

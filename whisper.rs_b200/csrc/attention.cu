@@ -73,8 +73,11 @@ constexpr uint32_t TMEM_COLS = 256;   // S0 | S1 | O: two CTAs fit the SM's 512 
 constexpr uint32_t TMEM_WG_STRIDE = 256;          // per warpgroup: S buffers at +0 and +64 (P over them), O at +128
 constexpr uint32_t TMEM_S = 0, TMEM_O = 128;
 constexpr float RESCALE_LOG2 = 8.0f;              // lazy rescale threshold: P stays below 2^8
-// of every 16 exponentials, those whose index bit is set here run on the FMA pipe (5 of 16)
-constexpr uint32_t POLY_MASK16 = (1u << 1) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13);
+// of every 16 key pairs (32 keys), those whose bit is set here run on the FMA pipe (5 of 16)
+#ifndef WB_ATTN_POLY_PAIR_MASK
+#define WB_ATTN_POLY_PAIR_MASK ((1u << 1) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13))
+#endif
+constexpr uint32_t POLY_PAIR_MASK = WB_ATTN_POLY_PAIR_MASK;
 
 struct AttnArgs {
   int B, T, H, n_kt, n_steps;
@@ -109,15 +112,23 @@ __device__ __noinline__ void rescale_o(uint32_t taddr_o, float alpha) {
   tmem_st_wait();
 }
 
-// P for 32 keys: 2^(c s - m c) as F16 pairs, element i (and its pair i + 1) in register i / 2
+// P for 32 keys: 2^(c s - m c) as F16 pairs, element i (and its pair i + 1) in register i / 2.
+// The scale-and-offset runs as packed FFMA2 (two keys per instruction); of every 16 key PAIRS, those
+// whose bit is set in POLY_PAIR_MASK evaluate both exponentials on the FMA pipe (packed cubic), the
+// rest go through the MUFU unit.
 __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float moff, uint32_t (&p)[16]) {
+  const uint64_t c2 = f2_pack(c, c), m2 = f2_pack(-moff, -moff);
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
-    const int i0 = 2 * u, i1 = i0 + 1;
-    const float x0 = fmaf(__uint_as_float(s[i0]), c, -moff);
-    const float x1 = fmaf(__uint_as_float(s[i1]), c, -moff);
-    const float e0 = ((POLY_MASK16 >> (i0 & 15)) & 1u) ? ex2_fma(x0) : ex2_mufu(x0);
-    const float e1 = ((POLY_MASK16 >> (i1 & 15)) & 1u) ? ex2_fma(x1) : ex2_mufu(x1);
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), c2, m2);
+    float x0, x1, e0, e1;
+    f2_unpack(x2, x0, x1);
+    if ((POLY_PAIR_MASK >> u) & 1u) {
+      ex2_fma_x2(x0, x1, e0, e1);
+    } else {
+      e0 = ex2_mufu(x0);
+      e1 = ex2_mufu(x1);
+    }
     p[u] = pack_h2(e0, e1);
   }
 }

@@ -358,6 +358,50 @@ __device__ __forceinline__ float ex2_fma(float x) {
   asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(r) : "r"(__float_as_int(t)), "r"(__float_as_int(p)));
   return __int_as_float(r);
 }
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 issue at the rate of the scalar forms, measured
+// tools/ubench/pipes.cu: 1.23 vs 1.39 warp-instr/clk/SM at 4 warps -- 1.77x the elements per issue slot)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// ex2_fma for two values at once: the magic-number split, the cubic and its Horner steps are packed
+// (7 issue slots + 2 clamps + 2 exponent IMADs for the pair, against 16 for two scalar evaluations)
+__device__ __forceinline__ void ex2_fma_x2(float x0, float x1, float& e0, float& e1) {
+  const uint64_t x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
+  const uint64_t t = f2_add(x, magic);
+  const uint64_t f = f2_sub(x, f2_sub(t, magic));
+  uint64_t p = f2_fma(f, f2_pack(0.0551716648f, 0.0551716648f), f2_pack(0.2426111251f, 0.2426111251f));
+  p = f2_fma(p, f, f2_pack(0.6932609677f, 0.6932609677f));
+  p = f2_fma(p, f, f2_pack(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  f2_unpack(t, t0, t1);
+  f2_unpack(p, p0, p1);
+  int r0, r1;
+  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(r0) : "r"(__float_as_int(t0)), "r"(__float_as_int(p0)));
+  asm("mad.lo.s32 %0, %1, 8388608, %2;" : "=r"(r1) : "r"(__float_as_int(t1)), "r"(__float_as_int(p1)));
+  e0 = __int_as_float(r0);
+  e1 = __int_as_float(r1);
+}
 // 3-input max (FMNMX3: same issue cost as the 2-input form, measured tools/ubench/pipes.cu)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
