@@ -55,6 +55,12 @@ struct Gemm2Args {
   int out_slab_cols;       // > 0: output column n lives in slab n / C at column n % C (out_map's third dimension)
   __half* vt_out;          // columns >= vt_col0 go to the transposed V buffer (see GemmEpilogue)
   int vt_col0, vt_heads, vt_head_rows, vt_ld, vt_T;
+  // LayerNorm folded into the GEMMs around it (see the LN template parameter)
+  float2* ln_stats_out;        // LN == 1: per-row (sum, sum of squares) of the f32 output, accumulated atomically
+  __half* x16_out;             // LN == 1: F16 copy of the f32 output [row][x16_ld] (the next GEMM's A operand)
+  int x16_ld;
+  const float2* ln_stats_in;   // LN == 2: the statistics of this GEMM's A rows
+  float ln_inv_d, ln_eps;
   long long* dbg;          // optional clock64() trace (CTA 0): [0,256) MMA warp, [256,1024) epilogue warp 4
 };
 #define G2_TRACE(cond, slot)                                   \
@@ -92,7 +98,15 @@ __device__ __forceinline__ Item item_coord(const Gemm2Args& a, int item) {
 // Epilogue variants are compile-time (F16 or f32 output, GELU, column scale, f32 residual): as run-time
 // flags the compiler predicated the unused paths off instruction by instruction -- the epilogue warps
 // still issued them, and at K = 512 the epilogue, not the tensor pipe, set the tile rate.
-template <int BN, bool F16O, bool GELU, bool CS, bool RES>
+//
+// LN: LayerNorm (galois_norm + repeat/mul/add, src/main.rs:1781-1785, 1882-1886, 1948-1952) folded into the two
+// GEMMs around it, so the normalised activations never make a round trip through HBM:
+//   LN == 1 (producer, with RES): the epilogue that writes the f32 residual stream x also writes an F16 copy of
+//           it and accumulates each row's sum and sum of squares (thread = row: two atomics per thread per tile);
+//   LN == 2 (consumer): A is that F16 copy and W' = W diag(gamma); with mu, rstd from the row statistics
+//           LN(x) W^T + b = rstd * (x W'^T - mu * c1) + c2,  c1[n] = sum_k W'[n][k],  c2[n] = sum_k W[n][k] beta[k] + b[n]
+//           (c1 arrives in the column-scale slot, c2 in the bias slot).
+template <int BN, bool F16O, bool GELU, bool CS, bool RES, int LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                          const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap res_map,
@@ -216,7 +230,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
     const int n_chunks_tile = BN / cw;
     const int my_nch = (n_chunks_tile - half + 1) / 2;   // chunks half, half+2, ...
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-    constexpr bool has_cs = CS;
+    constexpr bool has_cs = CS || LN == 2;   // LN == 2: the column-scale slot carries c1
     const int sw = lane & 7;
 
     // coordinates of this warp's chunk number `ci` (counted over all of its tiles)
@@ -263,6 +277,12 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           }
         }
       }
+      // LN fold: this thread's row of the tile (global row: the batch index is the slowest dimension); the
+      // consumer's row statistics are fetched here, under the accumulator wait, like the bias
+      const int ln_m = m_row0 + lane;
+      const long long ln_row = (long long)it.b * args.M_rows + ln_m;
+      float2 ln_st = make_float2(0.0f, 0.0f);
+      if (LN == 2 && ln_m < args.M_rows) ln_st = __ldg(args.ln_stats_in + ln_row);
       const bool tre = args.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
       G2_TRACE(tre, 256 + t * 16 + 0);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -279,6 +299,16 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
       }
       __syncwarp();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      float ln_rstd = 0.0f, ln_nmr = 0.0f;   // LN == 2: rstd and -mu * rstd of this row
+      float ln_s1 = 0.0f, ln_s2 = 0.0f;      // LN == 1: this thread's share of its row's statistics
+      if (LN == 2) {
+        const float mu = ln_st.x * args.ln_inv_d;
+        const float var = fmaxf(ln_st.y * args.ln_inv_d - mu * mu, 0.0f);
+        ln_rstd = rsqrtf(var + args.ln_eps);
+        ln_nmr = -mu * ln_rstd;
+      }
+      const uint64_t ln_rstd2 = f2_pack(ln_rstd, ln_rstd), ln_nmr2 = f2_pack(ln_nmr, ln_nmr);
+      uint64_t ln_s1p = 0, ln_s2p = 0;       // LN == 1: two-lane partial sums (FADD2 / FFMA2)
       if (my_nch == 0) {   // narrow tile: this warp has no chunk, but its arrival is counted
         tc_fence_before();
         if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
@@ -317,11 +347,20 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 bv = b4[g];
-            float x0 = __uint_as_float(r0[4 * g]) + bv.x, x1 = __uint_as_float(r0[4 * g + 1]) + bv.y;
-            float x2 = __uint_as_float(r0[4 * g + 2]) + bv.z, x3 = __uint_as_float(r0[4 * g + 3]) + bv.w;
-            if (has_cs) {
-              const float4 cv = c4[g];
-              x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+            float x0, x1, x2, x3;
+            if (LN == 2) {   // rstd * acc + (c2 - mu * rstd * c1)
+              const float4 cv = c4[g];   // packed FFMA2: two columns per instruction
+              const uint64_t t01 = f2_fma(ln_nmr2, f2_pack(cv.x, cv.y), f2_pack(bv.x, bv.y));
+              const uint64_t t23 = f2_fma(ln_nmr2, f2_pack(cv.z, cv.w), f2_pack(bv.z, bv.w));
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(r0[4 * g]), __uint_as_float(r0[4 * g + 1])), ln_rstd2, t01), x0, x1);
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(r0[4 * g + 2]), __uint_as_float(r0[4 * g + 3])), ln_rstd2, t23), x2, x3);
+            } else {
+              x0 = __uint_as_float(r0[4 * g]) + bv.x; x1 = __uint_as_float(r0[4 * g + 1]) + bv.y;
+              x2 = __uint_as_float(r0[4 * g + 2]) + bv.z; x3 = __uint_as_float(r0[4 * g + 3]) + bv.w;
+              if (has_cs) {
+                const float4 cv = c4[g];
+                x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+              }
             }
             if (GELU) {
               x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
@@ -333,11 +372,20 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const float4 bv = b4[8 + g];
-              float x0 = __uint_as_float(r1[4 * g]) + bv.x, x1 = __uint_as_float(r1[4 * g + 1]) + bv.y;
-              float x2 = __uint_as_float(r1[4 * g + 2]) + bv.z, x3 = __uint_as_float(r1[4 * g + 3]) + bv.w;
-              if (has_cs) {
+              float x0, x1, x2, x3;
+              if (LN == 2) {
                 const float4 cv = c4[8 + g];
-                x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+                const uint64_t t01 = f2_fma(ln_nmr2, f2_pack(cv.x, cv.y), f2_pack(bv.x, bv.y));
+                const uint64_t t23 = f2_fma(ln_nmr2, f2_pack(cv.z, cv.w), f2_pack(bv.z, bv.w));
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(r1[4 * g]), __uint_as_float(r1[4 * g + 1])), ln_rstd2, t01), x0, x1);
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(r1[4 * g + 2]), __uint_as_float(r1[4 * g + 3])), ln_rstd2, t23), x2, x3);
+              } else {
+                x0 = __uint_as_float(r1[4 * g]) + bv.x; x1 = __uint_as_float(r1[4 * g + 1]) + bv.y;
+                x2 = __uint_as_float(r1[4 * g + 2]) + bv.z; x3 = __uint_as_float(r1[4 * g + 3]) + bv.w;
+                if (has_cs) {
+                  const float4 cv = c4[8 + g];
+                  x0 *= cv.x; x1 *= cv.y; x2 *= cv.z; x3 *= cv.w;
+                }
               }
               if (GELU) {
                 x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
@@ -383,6 +431,18 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
             x.z += __uint_as_float(r0[4 * g + 2]); x.w += __uint_as_float(r0[4 * g + 3]);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
                          : "memory");
+            if (LN == 1) {   // statistics of the f32 values; their F16 copy replaces the accumulator registers
+              const uint64_t xa = f2_pack(x.x, x.y), xb = f2_pack(x.z, x.w);
+              ln_s1p = f2_add(ln_s1p, f2_add(xa, xb));
+              ln_s2p = f2_fma(xa, xa, f2_fma(xb, xb, ln_s2p));
+              r0[2 * g] = pack_h2(x.x, x.y);
+              r0[2 * g + 1] = pack_h2(x.z, x.w);
+            }
+          }
+          if (LN == 1 && ln_m < args.M_rows) {   // 32 columns = 64 bytes of this row (two full sectors)
+            uint4* dst = reinterpret_cast<uint4*>(args.x16_out + ln_row * args.x16_ld + n0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(r0[4 * v], r0[4 * v + 1], r0[4 * v + 2], r0[4 * v + 3]);
           }
         } else {
           // the store that last read this buffer (chunk ci - NBUF) must have finished reading it
@@ -427,6 +487,13 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
         __syncwarp();
         G2_TRACE(tre, 256 + t * 16 + 5 + k * 4);   // store issued (+ residual prefetch)
       }
+      if (LN == 1 && my_nch > 0 && ln_m < args.M_rows) {
+        float a0, a1, b0, b1;
+        f2_unpack(ln_s1p, a0, a1);
+        f2_unpack(ln_s2p, b0, b1);
+        atomicAdd(&args.ln_stats_out[ln_row].x, ln_s1 + a0 + a1);
+        atomicAdd(&args.ln_stats_out[ln_row].y, ln_s2 + b0 + b1);
+      }
     }
     if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the stores' reads
   }
@@ -439,7 +506,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
   }
 }
 
-template <int BN, bool F16O, bool GELU, bool CS, bool RES>
+template <int BN, bool F16O, bool GELU, bool CS, bool RES, int LN>
 cudaError_t launch_one(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -456,10 +523,10 @@ cudaError_t launch_one(const GemmProblem& g, const Gemm2Args& a, int grid, cudaS
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   // the kernel's opt-in to > 48 KB of dynamic shared memory, once per instantiation
-  static cudaError_t attr_err = cudaFuncSetAttribute(gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES>,
+  static cudaError_t attr_err = cudaFuncSetAttribute(gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES, LN>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
   if (attr_err != cudaSuccess) return attr_err;
-  return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES>, g.a_map, g.w_map, *g.out_map,
+  return cudaLaunchKernelEx(&cfg, gemm2_f16_tcgen05_kernel<BN, F16O, GELU, CS, RES, LN>, g.a_map, g.w_map, *g.out_map,
                             g.res_map ? *g.res_map : *g.out_map, a);
 }
 
@@ -467,8 +534,19 @@ template <int BN>
 cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
   const bool f16 = a.out_f16 != 0, gelu = a.gelu != 0, cs = a.colscale != nullptr || a.scale != 1.0f, res = a.has_res != 0;
   if (f16 && res) return cudaErrorInvalidValue;
+  const int ln = a.ln_stats_out ? 1 : a.ln_stats_in ? 2 : 0;
+  if (ln == 1) {   // producer of the folded LayerNorm: f32 residual stream out
+    if (f16 || !res || cs) return cudaErrorInvalidValue;
+    return gelu ? launch_one<BN, false, true, false, true, 1>(g, a, grid, st)
+                : launch_one<BN, false, false, false, true, 1>(g, a, grid, st);
+  }
+  if (ln == 2) {   // consumer: F16 out, c1 in the column-scale slot
+    if (!f16 || res || !a.colscale || a.scale != 1.0f) return cudaErrorInvalidValue;
+    return gelu ? launch_one<BN, true, true, false, false, 2>(g, a, grid, st)
+                : launch_one<BN, true, false, false, false, 2>(g, a, grid, st);
+  }
 #define WB_G2_CASE(F, G, C, R) \
-  if (f16 == F && gelu == G && cs == C && res == R) return launch_one<BN, F, G, C, R>(g, a, grid, st)
+  if (f16 == F && gelu == G && cs == C && res == R) return launch_one<BN, F, G, C, R, 0>(g, a, grid, st)
   WB_G2_CASE(true, false, false, false);
   WB_G2_CASE(true, true, false, false);
   WB_G2_CASE(true, false, true, false);
@@ -525,6 +603,12 @@ cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
   a.vt_head_rows = g.epi.vt_head_rows;
   a.vt_ld = g.epi.vt_ld;
   a.vt_T = g.epi.vt_T;
+  a.ln_stats_out = g.epi.ln_stats_out;
+  a.x16_out = g.epi.x16_out;
+  a.x16_ld = g.epi.x16_ld;
+  a.ln_stats_in = g.epi.ln_stats_in;
+  a.ln_inv_d = g.K > 0 ? 1.0f / (float)g.K : 0.0f;
+  a.ln_eps = g.epi.ln_eps;
   a.dbg = g.dbg;
   if (a.total_items <= 0) return cudaSuccess;
   const int max_pairs = num_sms / 2;

@@ -203,6 +203,8 @@ int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const
   // pair kernel: needs the output (and residual) tensor maps; a residual needs whole tiles of f32 output
   const bool pair = out_map && l.bn2 && !epi.transpose_out && !force_gemm1() && (!epi.residual || res_map) &&
                     (!res_map || (!epi.out_f16 && l.N % l.bn2 == 0 && epi.vt_col0 >= l.N));
+  if ((epi.ln_stats_out || epi.ln_stats_in) && !pair)
+    return fail_msg(ctx, WB_ERR_TENSOR_OP, "galois tensor:'LayerNorm-folded GEMM needs the pair kernel'");
   LaunchTimer t(ctx, family);
   if (pair) {
     g.w_map = l.map_w2;
@@ -349,6 +351,58 @@ int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>&
   return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
 }
 
+// A Linear whose input is LayerNorm(x) (gamma, beta), folded for the pair GEMM's LN == 2 epilogue:
+//   w = W diag(gamma) rounded to F16;  colscale = c1[n] = sum_k w[n][k];  bias = c2[n] = sum_k W[n][k] beta[k] + b[n]
+int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, const std::string& gamma,
+                  const std::string& beta, Linear& l) {
+  const HostTensor* gt = find(mv, gamma);
+  const HostTensor* bt = find(mv, beta);
+  if (!gt || !bt || gt->f16 || bt->f16) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + gamma + "'\n");
+  const float* g = reinterpret_cast<const float*>(gt->data);
+  const float* be = reinterpret_cast<const float*>(bt->data);
+  std::vector<__half> h;
+  std::vector<float> c1, c2;
+  int K = 0;
+  for (const CatPart& p : parts) {
+    const HostTensor* t = find(mv, p.w);
+    if (!t) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.w + "'\n");
+    if (p.scale != 1.0f) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: scaled part in an LN-folded weight");
+    std::vector<__half> part;
+    to_f16_host(*t, part);
+    K = (int)t->ne[0];
+    const int N = (int)t->ne[1];
+    if ((int64_t)K != gt->nelem() || (int64_t)K != bt->nelem())
+      return fail_msg(ctx, WB_ERR_WRONG_SHAPE_TENSOR, "tensor '" + gamma + "' has wrong shape in model file\n");
+    const float* pb = nullptr;
+    if (!p.b.empty()) {
+      const HostTensor* pbt = find(mv, p.b);
+      if (!pbt) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.b + "'\n");
+      pb = reinterpret_cast<const float*>(pbt->data);
+    }
+    for (int n = 0; n < N; ++n) {
+      double s1 = 0.0, s2 = 0.0;
+      __half* row = part.data() + (size_t)n * K;
+      for (int k = 0; k < K; ++k) {
+        const float w = __half2float(row[k]);
+        const __half wf = __float2half_rn(w * g[k]);
+        row[k] = wf;
+        s1 += (double)__half2float(wf);
+        s2 += (double)w * (double)be[k];
+      }
+      c1.push_back((float)s1);
+      c2.push_back((float)(s2 + (pb ? (double)pb[n] : 0.0)));
+    }
+    h.insert(h.end(), part.begin(), part.end());
+  }
+  l.K = K;
+  l.N = (int)(h.size() / (size_t)K);
+  int rc = upload_f16_vec(ctx, h, &l.w);
+  if (rc) return rc;
+  if ((rc = upload_f32_vec(ctx, c2, &l.bias))) return rc;
+  if ((rc = upload_f32_vec(ctx, c1, &l.colscale))) return rc;
+  return make_linear_maps(ctx, l, false) ? WB_OK : WB_ERR_TENSOR_OP;
+}
+
 int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
   const int n_mel = mv.filt_n_mel;
   if (mv.filt_n_fft != 201) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: mel filterbank must have 201 bins");
@@ -416,6 +470,7 @@ int alloc_activations(wb_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->h1, S * (Tm + 2) * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->x, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->ln_out, S * T * d))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->ln_stats, S * T * 2 * (size_t)hp.n_audio_layer + 1))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->qk, S * T * 2 * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vt, S * (d / 64) * ATTN_VT_HEAD_ROWS * ctx->Tp))) return rc;
   WB_CK(launch_vt_init(ctx->vt, (int)(S * (d / 64)), ctx->Tp, ctx->stream));
@@ -563,6 +618,13 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     if (rc) return bail(rc); \
   } while (0)
   TRY(build_mel_tables(ctx, mv));
+  {
+    // LayerNorm folded into the GEMMs around it (default; WB_LN_FOLD=0 keeps the separate LayerNorm kernel):
+    // needs the pair kernel for every GEMM involved
+    const char* ev = getenv("WB_LN_FOLD");
+    const int dd = hp.n_audio_state;
+    ctx->ln_fold = !(ev && ev[0] == '0') && !force_gemm1() && gemm2_pick_bn(dd) && gemm2_pick_bn(3 * dd) && gemm2_pick_bn(4 * dd);
+  }
   TRY(upload_f32(ctx, mv, "encoder.positional_embedding", &ctx->e_pe));
   TRY(upload_conv(ctx, mv, "encoder.conv1.weight", "encoder.conv1.bias", ctx->conv1));
   TRY(upload_conv(ctx, mv, "encoder.conv2.weight", "encoder.conv2.bias", ctx->conv2));
@@ -577,13 +639,17 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     TRY(upload_f32(ctx, mv, p + "mlp_ln.weight", &l.mlp_ln_w));
     TRY(upload_f32(ctx, mv, p + "mlp_ln.bias", &l.mlp_ln_b));
     // Q (+b), K (no bias), V (+b) fused into one [3d][d] weight (1891-1897)
-    TRY(upload_cat(ctx, mv,
-                   {{p + "attn.query.weight", p + "attn.query.bias", 1.0f},
-                    {p + "attn.key.weight", "", 1.0f},
-                    {p + "attn.value.weight", p + "attn.value.bias", 1.0f}},
-                   l.qkv, false));
+    const std::vector<CatPart> qkv_parts = {{p + "attn.query.weight", p + "attn.query.bias", 1.0f},
+                                            {p + "attn.key.weight", "", 1.0f},
+                                            {p + "attn.value.weight", p + "attn.value.bias", 1.0f}};
+    if (ctx->ln_fold) {   // attn_ln / mlp_ln folded into the weights that consume them (gemm2.cu, LN == 2)
+      TRY(upload_cat_ln(ctx, mv, qkv_parts, p + "attn_ln.weight", p + "attn_ln.bias", l.qkv));
+      TRY(upload_cat_ln(ctx, mv, {{p + "mlp.0.weight", p + "mlp.0.bias", 1.0f}}, p + "mlp_ln.weight", p + "mlp_ln.bias", l.fc1));
+    } else {
+      TRY(upload_cat(ctx, mv, qkv_parts, l.qkv, false));
+      TRY(upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, false));
+    }
     TRY(upload_linear(ctx, mv, p + "attn.out.weight", p + "attn.out.bias", l.out, false));
-    TRY(upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, false));
     TRY(upload_linear(ctx, mv, p + "mlp.2.weight", p + "mlp.2.bias", l.fc2, false));
   }
   {
@@ -941,6 +1007,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     return WB_OK;
   };
   int rc;
+  const bool fold = ctx->ln_fold;
+  const size_t ln_stride = (size_t)ctx->cfg.max_segments * T;   // rows per statistics slot
+  if (fold && L > 0) WB_CK(cudaMemsetAsync(ctx->ln_stats, 0, sizeof(float2) * ln_stride * 2 * L, st));
 
   // E0: mel window -> token-major F16 rows with zero padding rows (1816-1829)
   {
@@ -969,12 +1038,17 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     e.out_f16 = 0;
     e.out_bstride = (long long)T * d;
     e.out_ld = d;
+    if (fold && L > 0) {   // feeds attn_ln of layer 0
+      e.ln_stats_out = ctx->ln_stats;
+      e.x16_out = ctx->ln_out;
+      e.x16_ld = d;
+    }
     if ((rc = run_gemm(ctx, m_conv2, T, n_seg, ctx->conv2, e, "gemm_conv2", &o_x3, &o_pe, 1))) return rc;
     if (chk && (rc = probe_f32(2, ctx->x, (long long)T * d, (long long)T * d))) return rc;
   }
   for (int il = 0; il < L; ++il) {   // 1877-1975
     const EncLayer& l = ctx->enc[il];
-    {   // E4: attn_ln
+    if (!fold) {   // E4: attn_ln
       LaunchTimer t(ctx, "layernorm");
       WB_CK(launch_layernorm(ctx->x, l.attn_ln_w, l.attn_ln_b, M, d, ctx->ln_out, nullptr, st, 0, true));
     }
@@ -989,6 +1063,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.vt_head_rows = ATTN_VT_HEAD_ROWS;
       e.vt_ld = ctx->Tp;
       e.vt_T = T;
+      if (fold) e.ln_stats_in = ctx->ln_stats + (size_t)(2 * il) * ln_stride;
       if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e, "gemm_qkv", &o_qk))) return rc;
     }
     {   // E7: flash attention + head merge (1922-1929)
@@ -1002,9 +1077,14 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->x;
       e.out_f16 = 0;
       e.out_ld = d;
+      if (fold) {   // feeds mlp_ln
+        e.ln_stats_out = ctx->ln_stats + (size_t)(2 * il + 1) * ln_stride;
+        e.x16_out = ctx->ln_out;
+        e.x16_ld = d;
+      }
       if ((rc = run_gemm(ctx, m_att, M, 1, l.out, e, "gemm_out", &o_x, &o_x))) return rc;
     }
-    {   // E9: mlp_ln, fc1 + bias + GELU, fc2 + bias + residual (1948-1968)
+    if (!fold) {   // E9: mlp_ln, fc1 + bias + GELU, fc2 + bias + residual (1948-1968)
       LaunchTimer t(ctx, "layernorm");
       WB_CK(launch_layernorm(ctx->x, l.mlp_ln_w, l.mlp_ln_b, M, d, ctx->ln_out, nullptr, st, 0, true));
     }
@@ -1014,6 +1094,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->hidden;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
+      if (fold) e.ln_stats_in = ctx->ln_stats + (size_t)(2 * il + 1) * ln_stride;
       if ((rc = run_gemm(ctx, m_ln, M, 1, l.fc1, e, "gemm_fc1", &o_hid))) return rc;
     }
     {
@@ -1023,6 +1104,11 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->x;
       e.out_f16 = 0;
       e.out_ld = d;
+      if (fold && il + 1 < L) {   // feeds attn_ln of the next layer (ln_post keeps its own kernel: it has an f32 output)
+        e.ln_stats_out = ctx->ln_stats + (size_t)(2 * il + 2) * ln_stride;
+        e.x16_out = ctx->ln_out;
+        e.x16_ld = d;
+      }
       if ((rc = run_gemm(ctx, m_hid, M, 1, l.fc2, e, "gemm_fc2", &o_x, &o_x))) return rc;
     }
     if (chk && (rc = probe_f32(3 + il, ctx->x, (long long)T * d, (long long)T * d))) return rc;

@@ -99,7 +99,9 @@ struct wb_ctx {
   __half* conv_in = nullptr;          // [seg][Tm+2][n_mel]
   __half* h1 = nullptr;               // [seg][Tm+2][d]
   float* x = nullptr;                 // residual stream [seg*T][d] f32
-  __half* ln_out = nullptr;           // [seg*T][d]
+  __half* ln_out = nullptr;           // [seg*T][d]: LayerNorm output, or (ln_fold) the F16 copy of x
+  bool ln_fold = false;               // attn_ln / mlp_ln folded into the GEMMs around them (gemm2.cu LN template)
+  float2* ln_stats = nullptr;         // [2 L][max_segments*T] per-row (sum, sum of squares) of x, one slot per LN
   __half* qk = nullptr;               // [seg*T][2d]
   __half* vt = nullptr;               // [seg][H*64][Tp]
   __half* attn_out = nullptr;         // [seg*T][d]

@@ -66,6 +66,15 @@ struct GemmEpilogue {
   int vt_head_rows = 64;
   int vt_ld = 0;
   int vt_T = 1;
+  // LayerNorm folded into the GEMMs around it (pair kernel only, gemm2.cu): a producer (f32 residual-stream
+  // output) also writes an F16 copy x16_out[row*x16_ld + n] and accumulates per-row (sum, sum of squares) into
+  // ln_stats_out[row]; a consumer reads those statistics of its A rows (ln_stats_in, row width = K) and applies
+  // rstd * (acc - mu * colscale[n]) + bias[n].
+  float2* ln_stats_out = nullptr;
+  __half* x16_out = nullptr;
+  int x16_ld = 0;
+  const float2* ln_stats_in = nullptr;
+  float ln_eps = 1e-5f;
   // swap-AB mode for skinny activations (decoder): the GEMM computes C^T; element (m, n) is
   // stored at out[n*out_ld + m] and bias/colscale/residual are indexed by m instead of n.
   int transpose_out = 0;
