@@ -43,6 +43,24 @@ def test_micro_decode_logits_prompt_and_incremental(pkg, pyoracle, model_path, g
     ctx.close()
 
 
+def test_micro_long_prompt_many_rows(pkg, pyoracle, model_path, golden):
+    """More than 32 rows (sequences x prompt tokens) take the tcgen05 swap-AB GEMM with a plain LayerNorm in front
+    of the gamma-folded weights; up to 32 rows take the skinny kernel with the LayerNorm folded into its epilogue.
+    Both must give the oracle's logits, and a step after either prompt pass must agree."""
+    from whisper_rs_b200 import api
+    ctx, orcs = _setup(pkg, pyoracle, model_path, "micro", 2, int(golden["n_samples"]))
+    rng = np.random.default_rng(5)
+    toks = rng.integers(0, ctx.n_vocab - 1, size=(2, 20)).astype(np.int32)      # 40 rows
+    api.whisper_decode(ctx, toks, 0)
+    for s in range(2):
+        assert rel_l2(ctx.logits(s), orcs[s].decode(toks[s], 0)) < LOGIT_TOL, s
+    nxt = np.array([[3], [9]], dtype=np.int32)
+    api.whisper_decode(ctx, nxt, 20)                                            # 2 rows: folded path on that cache
+    for s in range(2):
+        assert rel_l2(ctx.logits(s), orcs[s].decode(nxt[s], 20)) < LOGIT_TOL, s
+    ctx.close()
+
+
 def test_micro_golden_logits(pkg, pyoracle, model_path, golden):
     from whisper_rs_b200 import api
     ctx, _ = _setup(pkg, pyoracle, model_path, "micro", 1, int(golden["n_samples"]))

@@ -57,17 +57,45 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
 
 // ---------------------------------------------------------------------------------------------
 // D1: x[s][i][:] = d_te[tok[s][i]][:] + d_pe[n_past + i][:]
-__global__ void embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
-                             int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x) {
+// With `stats` (the LayerNorm-folded single-token step): also leaves the row's (sum, sum of squares) in
+// stats[row] -- the statistics of layer 0's attn_ln -- and an F16 copy of the row, and block 0 clears the
+// other `n_clear` statistics slots of the step (their producers accumulate with atomics).
+__global__ void __launch_bounds__(128)
+embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
+             int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, float2* __restrict__ stats,
+             __half* __restrict__ x16, int n_clear) {
   pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
   pdl_launch_dependents();
+  __shared__ float red[2][4];
   const int row = blockIdx.x;   // s * n_tok + i
   const int i = row % n_tok;
   const int tok = tokens[row];
   const int pos = *n_past_p + i;
   const __half* e = te + (size_t)tok * d;
   const float* p = pe + (size_t)pos * d;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) x[(size_t)row * d + c] = __half2float(e[c]) + p[c];
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = __half2float(e[c]) + p[c];
+    x[(size_t)row * d + c] = v;
+    if (stats) {
+      x16[(size_t)row * d + c] = __float2half_rn(v);
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+  }
+  if (stats) {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = s1;
+      red[1][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      stats[row] = make_float2((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]), (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+    if (blockIdx.x == 0)
+      for (int c = threadIdx.x; c < n_clear; c += blockDim.x) stats[DEC_LN_ROWS + c] = make_float2(0.0f, 0.0f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -454,12 +482,22 @@ decode_linear_kernel(const DecodeLinear a) {
   // are written by 4 adjacent lanes as one contiguous run
   const int r = tid >> 2, f0 = (tid & 3) * 4;
   float v[4];
+  // LayerNorm folded into this layer (ln_in: statistics of the activation rows; the weights carry gamma):
+  //   rstd * (x w^T - mu * c1) + c2, c2 in the bias slot
+  float ln_rstd = 1.0f, ln_nmr = 0.0f;
+  if (a.ln_in) {
+    const float2 st = a.ln_in[min(r, a.R - 1)];
+    const float mu = st.x * a.ln_inv_d;
+    ln_rstd = rsqrtf(fmaxf(st.y * a.ln_inv_d - mu * mu, 0.0f) + a.ln_eps);
+    ln_nmr = -mu * ln_rstd;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int f = f0 + i;
     float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
     const int n = n0 + f;
     if (n < a.N) {
+      if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * a.ln_c1[n]);
       if (a.bias) x += a.bias[n];
       if (a.colscale) x *= a.colscale[n];
       x *= a.scale;
@@ -488,6 +526,35 @@ decode_linear_kernel(const DecodeLinear a) {
           if (a.out_f16) reinterpret_cast<__half*>(a.out)[(size_t)r * a.out_ld + n0 + f0 + i] = __float2half_rn(v[i]);
           else reinterpret_cast<float*>(a.out)[(size_t)r * a.out_ld + n0 + f0 + i] = v[i];
         }
+    }
+  }
+  if (a.ln_out) {   // producer of the next folded LayerNorm: row statistics of the f32 result + its F16 copy
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + f0 + i < a.N) {
+        s1 += v[i];
+        s2 = fmaf(v[i], v[i], s2);
+      }
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    if (r < a.R) {
+      if ((tid & 3) == 0) {
+        atomicAdd(&a.ln_out[r].x, s1);
+        atomicAdd(&a.ln_out[r].y, s2);
+      }
+      if (n0 + f0 + 3 < a.N) {
+        uint2 u;
+        u.x = pack_h2(v[0], v[1]);
+        u.y = pack_h2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(a.x16_out + (size_t)r * a.x16_ld + n0 + f0) = u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (n0 + f0 + i < a.N) a.x16_out[(size_t)r * a.x16_ld + n0 + f0 + i] = __float2half_rn(v[i]);
+      }
     }
   }
   if (a.top2) {   // per-CTA top-2 of every sequence over this CTA's 16 vocabulary entries
@@ -579,8 +646,11 @@ __global__ void advance_kernel(int* n_past, int add, int* step) {
 }  // namespace
 
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
-                         const int* n_past_dev, int d, float* x, cudaStream_t st) {
-  return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x);
+                         const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats, __half* x16,
+                         int n_clear) {
+  if (stats && n_seq * n_tok > DEC_LN_ROWS) return cudaErrorInvalidValue;
+  return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x, stats,
+                    x16, n_clear);
 }
 
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,

@@ -198,7 +198,7 @@ int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const
   g.N = l.N;
   g.K = l.K;
   if (!epi.bias) epi.bias = l.bias;
-  if (!epi.colscale) epi.colscale = l.colscale;
+  if (!epi.colscale) epi.colscale = epi.ln_stats_in ? l.ln_c1 : l.colscale;   // LN == 2 reads c1 from the column-scale slot
   g.epi = epi;
   // pair kernel: needs the output (and residual) tensor maps; a residual needs whole tiles of f32 output
   const bool pair = out_map && l.bn2 && !epi.transpose_out && !force_gemm1() && (!epi.residual || res_map) &&
@@ -351,10 +351,13 @@ int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>&
   return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
 }
 
-// A Linear whose input is LayerNorm(x) (gamma, beta), folded for the pair GEMM's LN == 2 epilogue:
-//   w = W diag(gamma) rounded to F16;  colscale = c1[n] = sum_k w[n][k];  bias = c2[n] = sum_k W[n][k] beta[k] + b[n]
+// A Linear whose input is LayerNorm(x) (gamma, beta), with the LayerNorm's affine part and the part's output
+// scale s folded into it:  w = s * W diag(gamma) rounded to F16;  ln_c1[n] = sum_k w[n][k];
+// bias = c2[n] = s * (sum_k W[n][k] beta[k] + b[n]).  Then
+//   s * (LN(x) W^T + b) = rstd * (x w^T - mu * ln_c1) + c2      (statistics applied in the GEMM epilogue), or
+//                       = xhat w^T + c2                          (xhat = (x - mu) * rstd from a plain LayerNorm kernel)
 int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, const std::string& gamma,
-                  const std::string& beta, Linear& l) {
+                  const std::string& beta, Linear& l, bool want_a_map) {
   const HostTensor* gt = find(mv, gamma);
   const HostTensor* bt = find(mv, beta);
   if (!gt || !bt || gt->f16 || bt->f16) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + gamma + "'\n");
@@ -366,7 +369,6 @@ int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPar
   for (const CatPart& p : parts) {
     const HostTensor* t = find(mv, p.w);
     if (!t) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.w + "'\n");
-    if (p.scale != 1.0f) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: scaled part in an LN-folded weight");
     std::vector<__half> part;
     to_f16_host(*t, part);
     K = (int)t->ne[0];
@@ -384,13 +386,13 @@ int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPar
       __half* row = part.data() + (size_t)n * K;
       for (int k = 0; k < K; ++k) {
         const float w = __half2float(row[k]);
-        const __half wf = __float2half_rn(w * g[k]);
+        const __half wf = __float2half_rn(p.scale * w * g[k]);
         row[k] = wf;
         s1 += (double)__half2float(wf);
         s2 += (double)w * (double)be[k];
       }
       c1.push_back((float)s1);
-      c2.push_back((float)(s2 + (pb ? (double)pb[n] : 0.0)));
+      c2.push_back((float)((double)p.scale * (s2 + (pb ? (double)pb[n] : 0.0))));
     }
     h.insert(h.end(), part.begin(), part.end());
   }
@@ -399,8 +401,8 @@ int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPar
   int rc = upload_f16_vec(ctx, h, &l.w);
   if (rc) return rc;
   if ((rc = upload_f32_vec(ctx, c2, &l.bias))) return rc;
-  if ((rc = upload_f32_vec(ctx, c1, &l.colscale))) return rc;
-  return make_linear_maps(ctx, l, false) ? WB_OK : WB_ERR_TENSOR_OP;
+  if ((rc = upload_f32_vec(ctx, c1, &l.ln_c1))) return rc;
+  return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
 }
 
 int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
@@ -643,8 +645,8 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
                                             {p + "attn.key.weight", "", 1.0f},
                                             {p + "attn.value.weight", p + "attn.value.bias", 1.0f}};
     if (ctx->ln_fold) {   // attn_ln / mlp_ln folded into the weights that consume them (gemm2.cu, LN == 2)
-      TRY(upload_cat_ln(ctx, mv, qkv_parts, p + "attn_ln.weight", p + "attn_ln.bias", l.qkv));
-      TRY(upload_cat_ln(ctx, mv, {{p + "mlp.0.weight", p + "mlp.0.bias", 1.0f}}, p + "mlp_ln.weight", p + "mlp_ln.bias", l.fc1));
+      TRY(upload_cat_ln(ctx, mv, qkv_parts, p + "attn_ln.weight", p + "attn_ln.bias", l.qkv, false));
+      TRY(upload_cat_ln(ctx, mv, {{p + "mlp.0.weight", p + "mlp.0.bias", 1.0f}}, p + "mlp_ln.weight", p + "mlp_ln.bias", l.fc1, false));
     } else {
       TRY(upload_cat(ctx, mv, qkv_parts, l.qkv, false));
       TRY(upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, false));

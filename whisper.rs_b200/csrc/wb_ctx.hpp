@@ -23,6 +23,9 @@ struct Linear {            // one weight matrix [N][K] f16 (row-major, K contigu
   CUtensorMap map_w2;      // dims {K, N}, box {64, bn2 / 2}: each CTA of a pair loads half of the W tile
   const float* bias = nullptr;
   const float* colscale = nullptr;
+  // LayerNorm-folded weights (upload_cat_ln): w = s * W diag(gamma), bias = c2 = s * (W beta + b),
+  // ln_c1[n] = sum_k w[n][k]:  s * (LN(x) W^T + b) = rstd * (x w^T - mu * ln_c1) + bias
+  const float* ln_c1 = nullptr;
 };
 
 struct EncLayer {
@@ -131,6 +134,8 @@ struct wb_ctx {
   float *d_margin = nullptr, *d_out_margin = nullptr;
   float *d_part_o = nullptr, *d_part_ml = nullptr;
   int dec_n_seq = 0;
+  const float *d_ones = nullptr, *d_zeros = nullptr;   // identity affine for the prompt pass's plain LayerNorm
+  float2* dec_ln_stats = nullptr;                // [3 Lt + 1][DEC_LN_ROWS] row statistics of the folded single-token step
   cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
   int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;
 

@@ -59,7 +59,10 @@ static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, in
 
 static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const ActMaps& act, int R, GemmEpilogue epi,
                            const char* family, float* top2) {
-  if (R > 32 || l.K % 64 != 0) return run_gemm_swapped(ctx, l, act, R, epi, family);
+  if (R > 32 || l.K % 64 != 0) {
+    if (epi.ln_stats_in || epi.ln_stats_out) return fail_msg(ctx, WB_ERR_TENSOR_OP, "galois tensor:'folded LayerNorm needs the skinny linear kernel'");
+    return run_gemm_swapped(ctx, l, act, R, epi, family);
+  }
   DecodeLinear a;
   a.w = l.w;
   a.x = x;
@@ -77,6 +80,17 @@ static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const 
   a.out_f16 = epi.out_f16;
   a.out_ld = epi.out_ld;
   a.top2 = top2;
+  if (epi.ln_stats_in) {   // folded LayerNorm, consumer side: l carries gamma (upload_cat_ln)
+    a.ln_in = epi.ln_stats_in;
+    a.ln_c1 = l.ln_c1;
+    a.ln_inv_d = 1.0f / (float)l.K;
+    a.ln_eps = epi.ln_eps;
+  }
+  if (epi.ln_stats_out) {  // producer side
+    a.ln_out = epi.ln_stats_out;
+    a.x16_out = epi.x16_out;
+    a.x16_ld = epi.x16_ld;
+  }
   LaunchTimer t(ctx, family);
   WB_CK(launch_decode_linear(a, ctx->stream));
   return WB_OK;
@@ -104,17 +118,23 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
     if ((rc = upload_f32(ctx, mv, p + "mlp_ln.weight", &l.mlp_ln_w))) return rc;
     if ((rc = upload_f32(ctx, mv, p + "mlp_ln.bias", &l.mlp_ln_b))) return rc;
     // Q = (Wq x + bq) * s ; K = (Wk x) * s ; V = Wv x + bv   (D2)
-    if ((rc = upload_cat(ctx, mv,
-                         {{p + "attn.query.weight", p + "attn.query.bias", s},
-                          {p + "attn.key.weight", "", s},
-                          {p + "attn.value.weight", p + "attn.value.bias", 1.0f}},
-                         l.qkv, true)))
+    // the three linears that read a LayerNorm carry its gamma / beta (and the Dh^-1/4 scale) in their weights:
+    // the single-token step applies the row statistics in the linear's epilogue (no LayerNorm kernel), the
+    // many-row prompt pass normalises with a plain LayerNorm (gamma = 1, beta = 0) in front of the same weights
+    if ((rc = upload_cat_ln(ctx, mv,
+                            {{p + "attn.query.weight", p + "attn.query.bias", s},
+                             {p + "attn.key.weight", "", s},
+                             {p + "attn.value.weight", p + "attn.value.bias", 1.0f}},
+                            p + "attn_ln.weight", p + "attn_ln.bias", l.qkv, true)))
       return rc;
     if ((rc = upload_linear(ctx, mv, p + "attn.out.weight", p + "attn.out.bias", l.out, true))) return rc;
-    if ((rc = upload_cat(ctx, mv, {{p + "cross_attn.query.weight", p + "cross_attn.query.bias", s}}, l.cq, true)))
+    if ((rc = upload_cat_ln(ctx, mv, {{p + "cross_attn.query.weight", p + "cross_attn.query.bias", s}},
+                            p + "cross_attn_ln.weight", p + "cross_attn_ln.bias", l.cq, true)))
       return rc;
     if ((rc = upload_linear(ctx, mv, p + "cross_attn.out.weight", p + "cross_attn.out.bias", l.cout, true))) return rc;
-    if ((rc = upload_linear(ctx, mv, p + "mlp.0.weight", p + "mlp.0.bias", l.fc1, true))) return rc;
+    if ((rc = upload_cat_ln(ctx, mv, {{p + "mlp.0.weight", p + "mlp.0.bias", 1.0f}}, p + "mlp_ln.weight", p + "mlp_ln.bias",
+                            l.fc1, true)))
+      return rc;
     if ((rc = upload_linear(ctx, mv, p + "mlp.2.weight", p + "mlp.2.bias", l.fc2, true))) return rc;
   }
   // ---- state
@@ -141,6 +161,12 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
   if ((rc = dev_alloc(ctx, &ctx->d_margin, (size_t)S))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_out_len, (size_t)S))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_done, (size_t)S))) return rc;
+  {
+    std::vector<float> ones((size_t)d, 1.0f), zeros((size_t)d, 0.0f);
+    if ((rc = upload_f32_vec(ctx, ones, &ctx->d_ones))) return rc;
+    if ((rc = upload_f32_vec(ctx, zeros, &ctx->d_zeros))) return rc;
+  }
+  if ((rc = dev_alloc(ctx, &ctx->dec_ln_stats, (size_t)DEC_LN_ROWS * (3 * Lt + 1)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_npast, 4))) return rc;
   ctx->d_step = ctx->d_npast + 1;
   // split-K cross-attention partials (only used for few rows: n_tok <= 8)
@@ -164,22 +190,30 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
   const long long ld_kv = d;   // cross K / V of one layer: dense [seg][T][d]
   cudaStream_t st = ctx->stream;
   int rc;
+  // few rows (the single-token step): LayerNorm folded into the linears around it -- the producers of the
+  // residual stream leave row statistics + an F16 copy (d_ln), the consumers apply them (slot 3 il + {0, 1, 2} =
+  // attn_ln, cross_attn_ln, mlp_ln of layer il).  Many rows (prompt pass on the tcgen05 GEMM): a LayerNorm
+  // kernel without affine part in front of the same folded weights.
+  const bool fold = R <= DEC_LN_ROWS && d % 64 == 0;
+  auto slot = [&](int i) { return ctx->dec_ln_stats + (size_t)i * DEC_LN_ROWS; };
   {
     LaunchTimer t(ctx, "dec_embed");
-    WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, ctx->dx, st));
+    WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, ctx->dx, st,
+                       fold ? ctx->dec_ln_stats : nullptr, ctx->d_ln, fold ? DEC_LN_ROWS * (3 * Lt) : 0));
   }
   const int n_split = n_tok <= 8 ? decode_cross_splits(n_seq, H, T, ctx->num_sms) : 1;
   for (int il = 0; il < Lt; ++il) {
     const DecLayer& l = ctx->dec[il];
-    {   // D2: self-attention
+    if (!fold) {   // D2: self-attention
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.attn_ln_w, l.attn_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
       e.out = ctx->d_qkv;
       e.out_f16 = 1;
       e.out_ld = 3 * d;
+      if (fold) e.ln_stats_in = slot(3 * il);
       if ((rc = run_linear_rows(ctx, l.qkv, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
@@ -195,17 +229,23 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
+      if (fold) {
+        e.ln_stats_out = slot(3 * il + 1);
+        e.x16_out = ctx->d_ln;
+        e.x16_ld = d;
+      }
       if ((rc = run_linear_rows(ctx, l.out, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
-    {   // D3: cross-attention over memory_cross_k/v written by wb_encode
+    if (!fold) {   // D3: cross-attention over memory_cross_k/v written by wb_encode
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.cross_ln_w, l.cross_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
       e.out = ctx->d_q;
       e.out_f16 = 1;
       e.out_ld = d;
+      if (fold) e.ln_stats_in = slot(3 * il + 1);
       if ((rc = run_linear_rows(ctx, l.cq, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
@@ -221,11 +261,16 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
+      if (fold) {
+        e.ln_stats_out = slot(3 * il + 2);
+        e.x16_out = ctx->d_ln;
+        e.x16_ld = d;
+      }
       if ((rc = run_linear_rows(ctx, l.cout, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
-    {   // D4: MLP
+    if (!fold) {   // D4: MLP
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, l.mlp_ln_w, l.mlp_ln_b, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
@@ -233,6 +278,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->d_hid;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
+      if (fold) e.ln_stats_in = slot(3 * il + 2);
       if ((rc = run_linear_rows(ctx, l.fc1, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
@@ -242,6 +288,11 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out = ctx->dx;
       e.out_f16 = 0;
       e.out_ld = d;
+      if (fold && il + 1 < Lt) {   // (decoder.ln in front of the logits keeps its kernel: d_te is shared with the embedding)
+        e.ln_stats_out = slot(3 * il + 3);
+        e.x16_out = ctx->d_ln;
+        e.x16_ld = d;
+      }
       if ((rc = run_linear_rows(ctx, l.fc2, ctx->d_hid, ctx->m_hid, R, e, "dec_gemm"))) return rc;
     }
   }
@@ -392,8 +443,9 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     if (n_past + 1 > n_ctx) break;   // text context full
     if (use_graph) {
       WB_CK(cudaGraphLaunch(ctx->step_graph, st));
-      // per layer: 3 LayerNorm + 6 linear + self-attn + cross-attn; + embed, final LN, logits, arg-max, advance
-      ctx->tm.n_kernel_launches += 11 * hp.n_text_layer + 5;
+      // per layer: 6 linear + self-attn + cross-attn (LayerNorm folded into the linears); + embed, final LN,
+      // logits, arg-max, advance
+      ctx->tm.n_kernel_launches += 8 * hp.n_text_layer + 5;
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");

@@ -70,6 +70,8 @@ struct CatPart {
   float scale;
 };
 int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, Linear& l, bool want_a_map);
+int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>& parts, const std::string& gamma,
+                  const std::string& beta, Linear& l, bool want_a_map);
 
 int decode_setup(wb_ctx* ctx, const ModelFileView& mv);   // wb_decode.cu: decoder weights + KV cache
 

@@ -153,7 +153,8 @@ cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long ro
 // n_past / step live in device memory so one captured CUDA graph serves every position.
 // D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
-                         const int* n_past_dev, int d, float* x, cudaStream_t st);
+                         const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats = nullptr,
+                         __half* x16 = nullptr, int n_clear = 0);
 // D2: append this step's K/V to the F16 cache [seq][n_text_ctx][d], causal attention over it
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
                                     const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st);
@@ -180,7 +181,15 @@ struct DecodeLinear {
   void* out = nullptr;             // [R][out_ld]
   int out_f16 = 1, out_ld = 0;
   float* top2 = nullptr;           // optional [R][n_parts][3]: per-CTA (top value, second value, index bits)
+  // LayerNorm folded into the single-token step (no LayerNorm kernels between the linears):
+  const float2* ln_in = nullptr;   // consumer: per-row (sum, sum of squares) of x; w carries gamma, bias = c2
+  const float* ln_c1 = nullptr;    //           c1[n] = sum_k w[n][k]
+  float ln_inv_d = 0.0f, ln_eps = 1e-5f;
+  float2* ln_out = nullptr;        // producer: statistics of the f32 result rows, accumulated atomically
+  __half* x16_out = nullptr;       //           and their F16 copy [R][x16_ld] (the next linear's activations)
+  int x16_ld = 0;
 };
+constexpr int DEC_LN_ROWS = 32;    // rows per statistics slot of the folded decode step
 cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st);
 int decode_linear_parts(int N);    // CTAs (= top-2 partials per sequence) for N output features
 cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
