@@ -28,6 +28,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 // streaming 16-byte load (read-only path, do not keep the line in L1)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;
   asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -410,8 +411,6 @@ constexpr int DL_ROWS = 16;       // weight rows (output features) per CTA
 
 __global__ void __launch_bounds__(DL_THREADS)
 decode_linear_kernel(const DecodeLinear a) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
   __shared__ float red[4][DL_ROWS][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane & 3, g = lane >> 2;
@@ -432,6 +431,42 @@ decode_linear_kernel(const DecodeLinear a) {
   // 4 k-blocks of fragments (24 x 16-byte loads per lane) are requested before the first MMA uses
   // them: the kernel is pure HBM / L2 latency otherwise
   constexpr int U = 4;
+  // ---- before the grid dependency resolves (programmatic dependent launch: this CTA is resident while the
+  // previous kernel of the step still runs): the weights do not depend on it, so this CTA's 16 weight rows are
+  // pulled into L2 and the first k-blocks into registers under the previous kernel.  The next kernel of the step
+  // may become resident right away (it blocks at its own wait until this grid has completed).
+  pdl_launch_dependents();
+  {
+    const int rows = min(DL_ROWS, a.N - n0);
+    const char* wbase = reinterpret_cast<const char*>(a.w + (size_t)n0 * a.K);
+    const size_t bytes = (size_t)rows * a.K * 2;
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)DL_THREADS * 128) prefetch_l2(wbase + off);
+  }
+  uint4 A0[U], B0[U];
+  const bool pre = k + 32 * U <= k_hi;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      A0[u] = ld_nc_v4(wa + k + 32 * u);
+      B0[u] = ld_nc_v4(wb + k + 32 * u);
+    }
+  }
+  pdl_wait();   // the activations (and the residual) are the previous kernel's output
+  if (pre) {
+    uint4 X[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) X[u][j] = *reinterpret_cast<const uint4*>(xg + (size_t)(8 * j) * a.ldx + k + 32 * u);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mma_16816(acc[j], A0[u].x, B0[u].x, A0[u].y, B0[u].y, X[u][j].x, X[u][j].y);
+        mma_16816(acc[j], A0[u].z, B0[u].z, A0[u].w, B0[u].w, X[u][j].z, X[u][j].w);
+      }
+    k += 32 * U;
+  }
   for (; k + 32 * U <= k_hi; k += 32 * U) {
     uint4 A[U], B[U], X[U][4];
 #pragma unroll
