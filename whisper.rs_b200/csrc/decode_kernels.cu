@@ -108,6 +108,7 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
 // second operand when the first (V) is F16.
 constexpr int SELF_THREADS = 128;
 constexpr int SELF_MAX_CTX = 448 + 64;
+constexpr int SELF_U = 8;          // key / value rows per lane requested before the first is used
 
 __global__ void __launch_bounds__(SELF_THREADS)
 decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restrict__ kc, __half* __restrict__ vc,
@@ -135,19 +136,28 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
     const int Tk = n_past + i + 1;            // causal: keys 0 .. n_past + i
     float q[8];
     unpack8(*reinterpret_cast<const uint4*>(qkv + (size_t)(s * n_tok + i) * 3 * d + h * DH + ch * 8), q);
-    for (int t0 = warp * 4; t0 < Tk; t0 += (SELF_THREADS / 32) * 4) {
-      const int t = t0 + sub;
-      float acc = 0.0f;
-      if (t < Tk) {
+    // SELF_U key rows per lane in flight (the loop is pure L2 / HBM latency otherwise)
+    constexpr int STRIDE = (SELF_THREADS / 32) * 4;
+    for (int t0 = warp * 4; t0 < Tk; t0 += STRIDE * SELF_U) {
+      uint4 kv[SELF_U];
+#pragma unroll
+      for (int u = 0; u < SELF_U; ++u) {
+        const int t = t0 + u * STRIDE + sub;
+        kv[u] = t < Tk ? *reinterpret_cast<const uint4*>(kbase + (size_t)t * d + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < SELF_U; ++u) {
+        const int t = t0 + u * STRIDE + sub;
         float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(kbase + (size_t)t * d + ch * 8), kf);
+        unpack8(kv[u], kf);
+        float acc = 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc = fmaf(q[j], kf[j], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (ch == 0 && t < Tk) sc[t] = acc;
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (ch == 0 && t < Tk) sc[t] = acc;
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -164,12 +174,19 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < Tk; t0 += (SELF_THREADS / 32) * 4) {
-      const int t = t0 + sub;
-      if (t < Tk) {
-        const float p = __half2float(__float2half_rn(sc[t] * inv));
+    for (int t0 = warp * 4; t0 < Tk; t0 += STRIDE * SELF_U) {
+      uint4 vv[SELF_U];
+#pragma unroll
+      for (int u = 0; u < SELF_U; ++u) {
+        const int t = t0 + u * STRIDE + sub;
+        vv[u] = t < Tk ? *reinterpret_cast<const uint4*>(vbase + (size_t)t * d + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < SELF_U; ++u) {
+        const int t = t0 + u * STRIDE + sub;
+        const float p = t < Tk ? __half2float(__float2half_rn(sc[t] * inv)) : 0.0f;
         float vf[8];
-        unpack8(*reinterpret_cast<const uint4*>(vbase + (size_t)t * d + ch * 8), vf);
+        unpack8(vv[u], vf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
       }
@@ -198,13 +215,12 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
 // n_split > 1 it emits (max, sum, unnormalised o) partials that cross_combine_kernel merges.
 constexpr int CROSS_THREADS = 256;
 constexpr int CROSS_MAX_SPAN = 1536;
+constexpr int CROSS_U = 8;
 
 __global__ void __launch_bounds__(CROSS_THREADS, 3)
 decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
-                         long long ld, int n_tok, int T, int span, __half* __restrict__ out,
+                         long long ld, long long head_stride, int n_tok, int T, int span, __half* __restrict__ out,
                          float* __restrict__ part_o, float* __restrict__ part_ml, int n_split) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
   __shared__ float sc[CROSS_MAX_SPAN];
   __shared__ float red[CROSS_THREADS / 32];
   __shared__ float opart[CROSS_THREADS / 32][4][DH];
@@ -212,23 +228,30 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane >> 3, ch = lane & 7;
   const int t_lo = sp * span, t_hi = min(T, t_lo + span), n = t_hi - t_lo;
-  const __half* kb = k + ((size_t)s * T + t_lo) * ld + h * DH + ch * 8;
-  const __half* vb = v + ((size_t)s * T + t_lo) * ld + h * DH + ch * 8;
+  const __half* kb = k + ((size_t)s * T + t_lo) * ld + h * head_stride + ch * 8;
+  const __half* vb = v + ((size_t)s * T + t_lo) * ld + h * head_stride + ch * 8;
+  // The encoder memory does not depend on the previous kernel of the step (only q does): this CTA's K rows
+  // (one 128-byte line each) are requested into L2 before the grid dependency resolves, i.e. under the
+  // latency-bound linear layer in front.
+  pdl_launch_dependents();
+  for (int t = tid; t < n; t += CROSS_THREADS) prefetch_l2(k + ((size_t)s * T + t_lo + t) * ld + h * head_stride);
+  pdl_wait();
   for (int i = 0; i < n_tok; ++i) {
     const int row = s * n_tok + i;
     float qf[8];
     unpack8(*reinterpret_cast<const uint4*>(q + (size_t)row * d + h * DH + ch * 8), qf);
-    // 4 independent 16-byte loads in flight per lane (the stream is pure HBM latency otherwise)
+    // CROSS_U independent 16-byte loads in flight per lane: with all 384 CTAs resident that is ~12 MB in flight,
+    // what HBM latency x bandwidth asks for (4 per lane measured 4.5 TB/s)
     constexpr int RPI = (CROSS_THREADS / 32) * 4;   // rows per CTA iteration
-    for (int t0 = warp * 4; t0 < n; t0 += 4 * RPI) {
-      uint4 kv[4];
+    for (int t0 = warp * 4; t0 < n; t0 += CROSS_U * RPI) {
+      uint4 kv[CROSS_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
         kv[u] = t < n ? ld_nc_v4(kb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
         float kf[8];
         unpack8(kv[u], kf);
@@ -256,15 +279,15 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < n; t0 += 4 * RPI) {
-      uint4 vv[4];
+    for (int t0 = warp * 4; t0 < n; t0 += CROSS_U * RPI) {
+      uint4 vv[CROSS_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
         vv[u] = t < n ? ld_nc_v4(vb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
         if (t < n) {
           const float p = __half2float(__float2half_rn(sc[t] * inv));   // P -> F16 before P.V
@@ -442,6 +465,15 @@ decode_linear_kernel(const DecodeLinear a) {
     const size_t bytes = (size_t)rows * a.K * 2;
     for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)DL_THREADS * 128) prefetch_l2(wbase + off);
   }
+  // the epilogue's per-feature constants are weights too: fetched here, not on the critical path after the MMAs
+  const int er = tid >> 2, ef0 = (tid & 3) * 4;          // epilogue mapping: row er, features ef0 .. ef0 + 3
+  const bool evec = n0 + ef0 + 3 < a.N;
+  float4 e_bias = make_float4(0.f, 0.f, 0.f, 0.f), e_c1 = e_bias, e_cs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (evec) {
+    if (a.bias) e_bias = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + ef0));
+    if (a.ln_in) e_c1 = __ldg(reinterpret_cast<const float4*>(a.ln_c1 + n0 + ef0));
+    if (a.colscale) e_cs = __ldg(reinterpret_cast<const float4*>(a.colscale + n0 + ef0));
+  }
   uint4 A0[U], B0[U];
   const bool pre = k + 32 * U <= k_hi;
   if (pre) {
@@ -452,6 +484,12 @@ decode_linear_kernel(const DecodeLinear a) {
     }
   }
   pdl_wait();   // the activations (and the residual) are the previous kernel's output
+  // residual row segment and row statistics: requested now, used after the MMAs
+  float4 e_res = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 e_st = make_float2(0.f, 0.f);
+  if (a.residual && er < a.R && evec && (a.res_ld & 3) == 0)
+    e_res = *reinterpret_cast<const float4*>(a.residual + (size_t)er * a.res_ld + n0 + ef0);
+  if (a.ln_in) e_st = a.ln_in[min(er, a.R - 1)];
   if (pre) {
     uint4 X[U][4];
 #pragma unroll
@@ -521,27 +559,40 @@ decode_linear_kernel(const DecodeLinear a) {
   //   rstd * (x w^T - mu * c1) + c2, c2 in the bias slot
   float ln_rstd = 1.0f, ln_nmr = 0.0f;
   if (a.ln_in) {
-    const float2 st = a.ln_in[min(r, a.R - 1)];
-    const float mu = st.x * a.ln_inv_d;
-    ln_rstd = rsqrtf(fmaxf(st.y * a.ln_inv_d - mu * mu, 0.0f) + a.ln_eps);
+    const float mu = e_st.x * a.ln_inv_d;
+    ln_rstd = rsqrtf(fmaxf(e_st.y * a.ln_inv_d - mu * mu, 0.0f) + a.ln_eps);
     ln_nmr = -mu * ln_rstd;
   }
+  if (evec && (!a.residual || (a.res_ld & 3) == 0)) {   // whole 4-feature group inside N: the prefetched constants
+    const float bb[4] = {e_bias.x, e_bias.y, e_bias.z, e_bias.w}, c1[4] = {e_c1.x, e_c1.y, e_c1.z, e_c1.w};
+    const float cs[4] = {e_cs.x, e_cs.y, e_cs.z, e_cs.w}, rs[4] = {e_res.x, e_res.y, e_res.z, e_res.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int f = f0 + i;
-    float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
-    const int n = n0 + f;
-    if (n < a.N) {
-      if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * a.ln_c1[n]);
-      if (a.bias) x += a.bias[n];
-      if (a.colscale) x *= a.colscale[n];
-      x *= a.scale;
+    for (int i = 0; i < 4; ++i) {
+      const int f = f0 + i;
+      float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
+      if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * c1[i]);
+      x = (x + bb[i]) * cs[i] * a.scale;
       if (a.gelu) x = gelu_f16in(x);
-      if (a.residual && r < a.R) x += a.residual[(size_t)r * a.res_ld + n];
-    } else {
-      x = -INFINITY;
+      v[i] = x + rs[i];
     }
-    v[i] = x;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = f0 + i;
+      float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
+      const int n = n0 + f;
+      if (n < a.N) {
+        if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * a.ln_c1[n]);
+        if (a.bias) x += a.bias[n];
+        if (a.colscale) x *= a.colscale[n];
+        x *= a.scale;
+        if (a.gelu) x = gelu_f16in(x);
+        if (a.residual && r < a.R) x += a.residual[(size_t)r * a.res_ld + n];
+      } else {
+        x = -INFINITY;
+      }
+      v[i] = x;
+    }
   }
   if (r < a.R) {
     if (n0 + f0 + 3 < a.N && (a.out_ld & 3) == 0) {
@@ -702,12 +753,12 @@ int decode_cross_splits(int n_seq, int H, int T, int num_sms) {
 }
 
 cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, const __half* v, long long ld_kv,
-                                     int n_seq, int n_tok, int T, int H, __half* out, float* part_o, float* part_ml,
-                                     int n_split, cudaStream_t st) {
+                                     long long head_stride, int n_seq, int n_tok, int T, int H, __half* out,
+                                     float* part_o, float* part_ml, int n_split, cudaStream_t st) {
   const int span = (T + n_split - 1) / n_split;
   if (span > CROSS_MAX_SPAN) return cudaErrorInvalidValue;
   cudaError_t e = launch_pdl(decode_cross_attn_kernel, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
-                             n_tok, T, span, out, part_o, part_ml, n_split);
+                             head_stride, n_tok, T, span, out, part_o, part_ml, n_split);
   if (e != cudaSuccess || n_split == 1) return e;
   return launch_pdl(cross_combine_kernel, dim3(H, n_seq * n_tok), dim3(DH), 0, st, part_o, part_ml, n_split, d, out);
 }

@@ -182,8 +182,17 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
 
 // One decode pass over `n_tok` new tokens per sequence: embed -> L x (self-attn, cross-attn, MLP)
 // -> final LN of the last position -> logits.  Launch-only (no host sync, no copies): capturable.
+// WB_DEC_SKIP (timing experiments only, results become meaningless): comma list of kernel families to leave out of
+// the step -- "cross", "self", "linear", "logits"
+static bool dec_skip(const char* what) {
+  const char* e = getenv("WB_DEC_SKIP");
+  return e && strstr(e, what) != nullptr;
+}
+
 static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok) {
   const ModelHParams& hp = ctx->hp;
+  const bool skip_cross = dec_skip("cross"), skip_self = dec_skip("self"), skip_lin = dec_skip("linear"),
+             skip_logits = dec_skip("logits");
   const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, T = hp.n_audio_ctx;
   const int n_ctx = hp.n_text_ctx;
   const int R = n_seq * n_tok;
@@ -214,9 +223,9 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out_f16 = 1;
       e.out_ld = 3 * d;
       if (fold) e.ln_stats_in = slot(3 * il);
-      if ((rc = run_linear_rows(ctx, l.qkv, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.qkv, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
-    {
+    if (!skip_self) {
       LaunchTimer t(ctx, "dec_self_attn");
       __half* kc = ctx->self_k + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
       __half* vc = ctx->self_v + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
@@ -234,7 +243,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
         e.x16_out = ctx->d_ln;
         e.x16_ld = d;
       }
-      if ((rc = run_linear_rows(ctx, l.out, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.out, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
     if (!fold) {   // D3: cross-attention over memory_cross_k/v written by wb_encode
       LaunchTimer t(ctx, "dec_layernorm");
@@ -246,13 +255,16 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out_f16 = 1;
       e.out_ld = d;
       if (fold) e.ln_stats_in = slot(3 * il + 1);
-      if ((rc = run_linear_rows(ctx, l.cq, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.cq, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
-    {
+    if (!skip_cross) {
       LaunchTimer t(ctx, "dec_cross_attn");
       const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab;
-      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + ctx->cross_slab, ld_kv, n_seq, n_tok, T, H, ctx->d_att, ctx->d_part_o,
-                                     ctx->d_part_ml, n_split, st));
+      // (timing experiment WB_DEC_SKIP=headmajor: read the slab as if it were head-major -- garbage results)
+      const bool hm = dec_skip("headmajor");
+      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + ctx->cross_slab, hm ? 64 : ld_kv,
+                                     hm ? (long long)ctx->cfg.max_segments * T * 64 : 64, n_seq, n_tok, T, H, ctx->d_att,
+                                     ctx->d_part_o, ctx->d_part_ml, n_split, st));
     }
     {
       GemmEpilogue e;
@@ -266,7 +278,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
         e.x16_out = ctx->d_ln;
         e.x16_ld = d;
       }
-      if ((rc = run_linear_rows(ctx, l.cout, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.cout, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
     }
     if (!fold) {   // D4: MLP
       LaunchTimer t(ctx, "dec_layernorm");
@@ -279,7 +291,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       e.out_f16 = 1;
       e.out_ld = 4 * d;
       if (fold) e.ln_stats_in = slot(3 * il + 2);
-      if ((rc = run_linear_rows(ctx, l.fc1, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc1, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
     }
     {
       GemmEpilogue e;
@@ -293,7 +305,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
         e.x16_out = ctx->d_ln;
         e.x16_ld = d;
       }
-      if ((rc = run_linear_rows(ctx, l.fc2, ctx->d_hid, ctx->m_hid, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc2, ctx->d_hid, ctx->m_hid, R, e, "dec_gemm"))) return rc;
     }
   }
   {   // D5: logits of the last position of every sequence
@@ -308,8 +320,8 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
     e.out_ld = hp.n_vocab;
     // <= 32 sequences: the skinny kernel also leaves per-CTA top-2 partials, so D6 never re-reads the logits
     ctx->logits_top2_valid = n_seq <= 32 && ctx->logits_lin.K % 64 == 0;
-    if ((rc = run_linear_rows(ctx, ctx->logits_lin, ctx->d_lnf, ctx->m_lnf, n_seq, e, "dec_gemm_logits",
-                              ctx->logits_top2_valid ? ctx->d_top2 : nullptr)))
+    if (!skip_logits && (rc = run_linear_rows(ctx, ctx->logits_lin, ctx->d_lnf, ctx->m_lnf, n_seq, e, "dec_gemm_logits",
+                                              ctx->logits_top2_valid ? ctx->d_top2 : nullptr)))
       return rc;
   }
   return WB_OK;
