@@ -429,16 +429,21 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int DL_THREADS = 128;   // 4 warps: K split four ways
+// NW warps split K (4 for K <= 768, 8 beyond); U = 32-wide k-blocks per lane requested together -- the first U
+// before the grid dependency resolves.  With K / NW = 32 U every weight of the CTA is in flight before the
+// previous kernel has finished and the activations arrive in one batch: one exposed L2 round trip instead
+// of one per loop iteration (the step is a chain of ~100 such latency-bound kernels).
 constexpr int DL_ROWS = 16;       // weight rows (output features) per CTA
 
-__global__ void __launch_bounds__(DL_THREADS)
+template <int U, int NW>
+__global__ void __launch_bounds__(32 * NW)
 decode_linear_kernel(const DecodeLinear a) {
-  __shared__ float red[4][DL_ROWS][33];
+  constexpr int DL_THREADS = 32 * NW;
+  __shared__ float red[NW][DL_ROWS][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane & 3, g = lane >> 2;
   const int n0 = blockIdx.x * DL_ROWS;
-  const int kw = a.K / 4;                       // this warp's K range (multiple of 16)
+  const int kw = a.K / NW;                      // this warp's K range (multiple of 16)
   const int k_lo = warp * kw, k_hi = k_lo + kw;
   // rows past N (ragged vocabulary) are clamped for the loads and masked at the store
   const int ra = min(n0 + g, a.N - 1), rb = min(n0 + g + 8, a.N - 1);
@@ -453,7 +458,6 @@ decode_linear_kernel(const DecodeLinear a) {
   int k = k_lo;
   // 4 k-blocks of fragments (24 x 16-byte loads per lane) are requested before the first MMA uses
   // them: the kernel is pure HBM / L2 latency otherwise
-  constexpr int U = 4;
   // ---- before the grid dependency resolves (programmatic dependent launch: this CTA is resident while the
   // previous kernel of the step still runs): the weights do not depend on it, so this CTA's 16 weight rows are
   // pulled into L2 and the first k-blocks into registers under the previous kernel.  The next kernel of the step
@@ -551,6 +555,7 @@ decode_linear_kernel(const DecodeLinear a) {
     red[warp][g + 8][8 * j + 2 * t + 1] = acc[j][3];
   }
   __syncthreads();
+  if (tid >= 128) return;   // (warp-uniform) the epilogue is 32 rows x 4 feature groups
   // ---- epilogue: thread -> (row r = tid / 4, features f = 4 (tid % 4) .. +3): a row's 16 features
   // are written by 4 adjacent lanes as one contiguous run
   const int r = tid >> 2, f0 = (tid & 3) * 4;
@@ -569,7 +574,9 @@ decode_linear_kernel(const DecodeLinear a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int f = f0 + i;
-      float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
+      float x = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) x += red[w][f][r];
       if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * c1[i]);
       x = (x + bb[i]) * cs[i] * a.scale;
       if (a.gelu) x = gelu_f16in(x);
@@ -579,7 +586,9 @@ decode_linear_kernel(const DecodeLinear a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int f = f0 + i;
-      float x = red[0][f][r] + red[1][f][r] + red[2][f][r] + red[3][f][r];
+      float x = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) x += red[w][f][r];
       const int n = n0 + f;
       if (n < a.N) {
         if (a.ln_in) x = fmaf(x, ln_rstd, ln_nmr * a.ln_c1[n]);
@@ -773,7 +782,25 @@ cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next
 
 cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st) {
   if (a.R < 1 || a.R > 32 || a.N < 1 || a.K % 64 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
-  return launch_pdl(decode_linear_kernel, dim3((a.N + DL_ROWS - 1) / DL_ROWS), dim3(DL_THREADS), 0, st, a);
+  const dim3 grid((a.N + DL_ROWS - 1) / DL_ROWS);
+#define WB_DL(U, NW) \
+  if (a.K % (32 * (U) * (NW)) == 0 || ((U) == 4 && (NW) == 4)) return launch_pdl(decode_linear_kernel<U, NW>, grid, dim3(32 * (NW)), 0, st, a)
+  if (a.K <= 768) {          // 4 warps, every k-block of the CTA in flight at once when K = 128 U
+    if (a.K == 768) WB_DL(6, 4);
+    if (a.K == 640) WB_DL(5, 4);
+    if (a.K == 384) WB_DL(3, 4);
+    if (a.K == 256) WB_DL(2, 4);
+    if (a.K == 128) WB_DL(1, 4);
+    WB_DL(4, 4);             // 512, and any other K (looped)
+  }
+  if (a.K % 64 == 0) {       // K > 768: 8 warps (kw multiple of 8... the 16-wide tail needs kw % 16 == 0)
+    if (a.K % (8 * 32 * 6) == 0) WB_DL(6, 8);   // 1536, 3072, 4608
+    if (a.K % (8 * 32 * 5) == 0) WB_DL(5, 8);   // 1280, 2560, 5120
+    if (a.K % (8 * 32 * 4) == 0) WB_DL(4, 8);   // 1024, 2048, 4096
+  }
+  WB_DL(4, 4);
+#undef WB_DL
+  return cudaErrorInvalidValue;
 }
 int decode_linear_parts(int N) { return (N + DL_ROWS - 1) / DL_ROWS; }
 
