@@ -63,6 +63,9 @@ extern "C" {
     pub fn wb_pcm_to_mel_device(ctx: *mut wb_ctx, pcm_dev: *const f32, n_samples: usize, n_clips: c_int) -> c_int;
     pub fn wb_pcm16_to_mel(ctx: *mut wb_ctx, pcm: *const i16, n_samples: usize, n_clips: c_int) -> c_int;
     pub fn wb_pcm_prefetch(ctx: *mut wb_ctx, pcm: *const c_void, n_bytes: usize) -> c_int;
+    pub fn wb_pcm_to_logmel(ctx: *mut wb_ctx, pcm: *const f32, n_samples: usize, n_clips: c_int, n_frames: c_int) -> c_int;
+    pub fn wb_mel_max_read(ctx: *mut wb_ctx, out: *mut f32, n_clips: c_int) -> c_int;
+    pub fn wb_mel_normalize(ctx: *mut wb_ctx, clip_max: *const f32, n_clips: c_int) -> c_int;
     pub fn wb_mel_dims(ctx: *const wb_ctx, n_mel: *mut c_int, n_len: *mut c_int, n_clips: *mut c_int) -> c_int;
     pub fn wb_mel_read(ctx: *mut wb_ctx, clip: c_int, out: *mut f32, cap_floats: usize) -> c_int;
     pub fn wb_mel_write(ctx: *mut wb_ctx, mel: *const f32, n_mel: c_int, n_len: c_int, n_clips: c_int) -> c_int;
@@ -71,6 +74,8 @@ extern "C" {
     pub fn wb_cross_kv_read(ctx: *mut wb_ctx, seg: c_int, layer: c_int, k: *mut u16, v: *mut u16) -> c_int;
     pub fn wb_checksum(ctx: *mut wb_ctx, stage: c_int, layer: c_int, seg: c_int, abs_sum: *mut f64) -> c_int;
     pub fn wb_encoder_digest(ctx: *mut wb_ctx, out: *mut f64, cap: c_int) -> c_int;
+    pub fn wb_encoder_digest_async(ctx: *mut wb_ctx, out: *mut f64, cap: c_int) -> c_int;
+    pub fn wb_wait(ctx: *mut wb_ctx, ticket: c_int) -> c_int;
     pub fn wb_decode(ctx: *mut wb_ctx, tokens: *const i32, n_tokens: c_int, n_past: c_int, n_seqs: c_int) -> c_int;
     pub fn wb_logits_read(ctx: *mut wb_ctx, seq: c_int, out: *mut f32) -> c_int;
     pub fn wb_decode_greedy(ctx: *mut wb_ctx, prompt: *const i32, n_prompt: c_int, max_new: c_int, eot: c_int,

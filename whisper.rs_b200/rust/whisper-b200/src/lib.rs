@@ -140,6 +140,21 @@ pub fn whisper_pcm_to_mel(ctx: &mut WhisperContext, samples: Arc<Vec<f32>>) -> W
     check(unsafe { sys::wb_pcm_to_mel(ctx.h, samples.as_ptr(), samples.len(), 1) }, ctx.h)
 }
 
+/// Phase 1 of `whisper_pcm_to_mel` for one part of a clip that is split across GPUs: log10 mel
+/// (src/main.rs:1554-1652) of exactly `n_frames` frames of `samples`; returns this part's maximum
+/// (the partial result of the scan at 1655-1662).
+pub fn whisper_pcm_to_logmel(ctx: &mut WhisperContext, samples: &[f32], n_frames: usize) -> WsResult<f32> {
+    check(unsafe { sys::wb_pcm_to_logmel(ctx.h, samples.as_ptr(), samples.len(), 1, n_frames as i32) }, ctx.h)?;
+    let mut mx = 0f32;
+    check(unsafe { sys::wb_mel_max_read(ctx.h, &mut mx, 1) }, ctx.h)?;
+    Ok(mx)
+}
+
+/// Phase 2: `clamp_and_normalize` (src/main.rs:1654-1671) with the maximum over every part of the clip.
+pub fn whisper_mel_normalize(ctx: &mut WhisperContext, clip_max: f32) -> WsResult<()> {
+    check(unsafe { sys::wb_mel_normalize(ctx.h, &clip_max, 1) }, ctx.h)
+}
+
 /// src/main.rs:1799 -- `n_threads` is accepted and ignored, exactly as in the reference.
 pub fn whisper_encode(wctx: &mut WhisperContext, _n_threads: usize, mel_offset: usize) -> WsResult<()> {
     let off = [mel_offset];
