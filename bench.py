@@ -453,6 +453,11 @@ def run_gpu(args, pkg, rank: int, world: int, local_rank: int):
                 "launches_per_step": gemm_n / K, "avg_launch_us": gemm_us / gemm_n if gemm_n else None,
                 "share_of_step": shares.get("gemm"),
                 "algorithmic_flops_per_segment": fl["gemm"],
+                # the per-launch event brackets drain the stream (the bracketed pass is slower than the timed step);
+                # the same FLOPs over this family's share of the UNbracketed step time, for comparison only
+                "achieved_from_share_of_unbracketed_step":
+                    (fl["gemm"] * B) / (shares["gemm"] / sum(shares.values()) * (ms_dev / K) * 1e-3) / 1e12
+                    if shares.get("gemm") else None,
             },
             "kernels": {
                 "attention": {"tflops": att_tf, "frac_of_peak": att_tf / peak_tf if peak_tf else None,

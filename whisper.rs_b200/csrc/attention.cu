@@ -174,7 +174,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       mbar_init(&bar_done[i], 1);
       for (int k = 0; k < 2; ++k) {
         mbar_init(&bar_s[i * 2 + k], 1);
-        mbar_init(&bar_p[i * 2 + k], QT);
+        mbar_init(&bar_p[i * 2 + k], QT / 32);   // one arrival per softmax warp
       }
     }
     for (int i = 0; i < NS; ++i) {
@@ -327,7 +327,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       }
       tmem_st_wait();
       tc_fence_before();   // TMEM accesses ordered before the MMAs the MMA warp issues
-      mbar_arrive(&bar_p[g * 2 + sb]);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&bar_p[g * 2 + sb]);   // (128 arrivals on one barrier word serialise in the shared-memory atomic unit)
       ATTN_TRACE((j * 2 + g) * 8 + 4);
     };
 #pragma unroll 1

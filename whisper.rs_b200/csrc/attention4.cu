@@ -1,0 +1,322 @@
+// attention4.cu -- the fused softmax attention of attention.cu re-cut with ONE score buffer per CTA, so that
+// more than two CTAs share an SM (sm_100a).  Selected with WB_ATTN4=1; attention.cu stays the default.
+//
+// Same operation and numerics contract as attention.cu (galois_flash_attn, src/main.rs:1787-1797, call
+// 1922, and the repack / permute / merge ops 1898-1929): Q, K, V rounded to F16, probabilities F16 in the
+// P.V product, scores / running max / exponent argument / all accumulation in f32.
+//
+// Why this cut was tried: at Dh = 64 attention.cu is not bound by the tensor pipe (34 % active) or by MUFU
+// throughput (-26 % instructions per step bought +5 %, the MUFU : FMA split is flat) -- the suspicion was the
+// dependency chain of a softmax step with only two softmax warps per scheduler.  A CTA of attention.cu needs
+// 256 TMEM columns (two score buffers + an 80-column accumulator whose 65th column is the softmax
+// denominator), which caps the SM at two CTAs.  Here a CTA keeps one 64-column score buffer and a 64-column
+// accumulator (128 columns) and 48 KB of shared memory (Q + two 64-key K / V^T stages); the denominator moves
+// to the CUDA cores (one packed FADD2 per key pair); a CTA's next scores can only be issued behind the P.V
+// that consumes the buffer, and that latency is meant to hide under the other CTAs of the SM.
+//
+// Measured on B200 (base, 16 segments, per-launch CUDA events, attention.cu = 551 TFLOP/s):
+//   4 CTAs / SM, 80 registers, the 64 scores of a row read from TMEM twice (32 at a time)   539 TFLOP/s
+//   3 CTAs / SM, 96 registers, one TMEM pass (this file)                                    510 TFLOP/s
+// i.e. more resident softmax warps do not help.  TMEM reads run at 64 B/clk/SM (B300_MICROARCH.md): a pass
+// over a 128 x 64 f32 score tile costs 512 cycles, so the two-pass variant sits at 90 % of its TMEM-read
+// bound (1024 cycles per step against ~1130 measured), and every one-pass variant (this one, attention.cu)
+// spends half of its ~1100 cycles per step on that pass alone -- the read of the scores, not the exponentials,
+// is the first-order cost at Dh = 64.
+#include "ptx.cuh"
+#include "wb_kernels.hpp"
+
+namespace wb {
+
+namespace {
+
+constexpr int QT = 128;   // queries per CTA
+constexpr int KS = 64;    // keys per step = per stage
+constexpr int DH = 64;
+constexpr int NS = 2;     // K / V^T stages
+constexpr int TILE_Q_BYTES = QT * DH * 2;   // 16 KB
+constexpr int TILE_K_BYTES = KS * DH * 2;   // 8 KB: 64 key rows of 128 bytes
+constexpr int TILE_V_BYTES = DH * KS * 2;   // 8 KB: 64 head rows of 64 keys (V^T, time contiguous)
+constexpr int SMEM_Q = 0;
+constexpr int SMEM_K = SMEM_Q + TILE_Q_BYTES;
+constexpr int SMEM_V = SMEM_K + NS * TILE_K_BYTES;
+constexpr int SMEM_BAR = SMEM_V + NS * TILE_V_BYTES;
+constexpr int ATTN4_SMEM_BYTES = SMEM_BAR + 128;
+constexpr int MMA_WARP = 4, TMA_WARP = 5;
+constexpr int ATTN4_THREADS = 192;
+constexpr int ATTN4_CTAS_PER_SM = 3;   // 112 registers per thread: the row's 64 scores stay in registers
+constexpr uint32_t TMEM_COLS = 128;   // S | O
+constexpr uint32_t TMEM_S = 0, TMEM_O = 64;
+constexpr float RESCALE_LOG2 = 8.0f;  // lazy rescale threshold: P stays below 2^8
+// of every 16 key pairs (32 keys), those whose bit is set here run on the FMA pipe
+constexpr uint32_t POLY_PAIR_MASK = (1u << 1) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13);
+
+template <bool B>
+struct BoolTagT {
+  static constexpr bool value = B;
+};
+
+struct Attn4Args {
+  int B, T, H, n_steps;
+  __half* out;
+  float scale_log2;   // scale * log2(e)
+};
+
+// O[row][0..63] *= alpha (rare after the first steps; not inlined, see attention.cu)
+__device__ __noinline__ void rescale_o4(uint32_t taddr_o, float alpha) {
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t o[16];
+    tmem_ld_32x32b_x16(taddr_o + cc * 16, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_32x32b_x16(taddr_o + cc * 16, o);
+  }
+  tmem_st_wait();
+}
+
+// P for 32 keys: 2^(c s - m c) as F16 pairs (register u = keys 2u, 2u + 1); the f32 values are also added
+// into the two-lane running denominator
+__device__ __forceinline__ void exp_chunk4(const uint32_t (&s)[32], float c, float moff, uint32_t (&p)[16], uint64_t& l2) {
+  const uint64_t c2 = f2_pack(c, c), m2 = f2_pack(-moff, -moff);
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), c2, m2);
+    float x0, x1, e0, e1;
+    f2_unpack(x2, x0, x1);
+    if ((POLY_PAIR_MASK >> u) & 1u) {
+      ex2_fma_x2(x0, x1, e0, e1);
+    } else {
+      e0 = ex2_mufu(x0);
+      e1 = ex2_mufu(x1);
+    }
+    l2 = f2_add(l2, f2_pack(e0, e1));
+    p[u] = pack_h2(e0, e1);
+  }
+}
+
+__device__ __forceinline__ float max_chunk4(const uint32_t (&s)[32]) {
+  float m[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(__uint_as_float(s[u]), __uint_as_float(s[4 + u]), __uint_as_float(s[8 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(m[u], __uint_as_float(s[12 + u]), __uint_as_float(s[16 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmax3(m[u], __uint_as_float(s[20 + u]), __uint_as_float(s[24 + u]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) m[u] = fmaxf(m[u], __uint_as_float(s[28 + u]));
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+
+__global__ void __launch_bounds__(ATTN4_THREADS, ATTN4_CTAS_PER_SM)
+attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __grid_constant__ CUtensorMap vt_map,
+                          const Attn4Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);   // Q tile landed
+  uint64_t* bar_kfull = bar_q + 1;       // [NS] K stage landed
+  uint64_t* bar_vfull = bar_kfull + NS;  // [NS] V stage landed
+  uint64_t* bar_free = bar_vfull + NS;   // [NS] the P.V that read the stage has retired (its S retired earlier)
+  uint64_t* bar_s = bar_free + NS;       // scores written (and every earlier MMA retired: O is idle)
+  uint64_t* bar_p = bar_s + 1;           // P written over the score buffer (128 arrivals)
+  uint64_t* bar_done = bar_p + 1;        // last P.V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int H = a.H, T = a.T, n_steps = a.n_steps;
+  const int q0 = blockIdx.x * QT;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, QT / 32);   // one arrival per softmax warp
+    mbar_init(bar_done, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bar_kfull[i], 1);
+      mbar_init(&bar_vfull[i], 1);
+      mbar_init(&bar_free[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
+
+  if (warp == TMA_WARP) {
+    // ===================== TMA loads, one thread =====================
+    if ((tid & 31) == 0) {
+      prefetch_tmap(&qk_map);
+      prefetch_tmap(&vt_map);
+      const int vrow = (b * H + h) * ATTN_VT_HEAD_ROWS;   // the head's 64 V^T rows (the ones / zero rows behind them are not read)
+      mbar_arrive_expect_tx(bar_q, TILE_Q_BYTES);
+      tma_load_4d(smem + SMEM_Q, &qk_map, bar_q, 0, h, q0, b);                           // 64-row boxes
+      tma_load_4d(smem + SMEM_Q + TILE_Q_BYTES / 2, &qk_map, bar_q, 0, h, q0 + 64, b);
+      for (int j = 0; j < n_steps; ++j) {
+        const int st = j % NS;
+        if (j >= NS) mbar_wait(&bar_free[st], ((j / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_kfull[st], TILE_K_BYTES);
+        tma_load_4d(smem + SMEM_K + st * TILE_K_BYTES, &qk_map, &bar_kfull[st], 0, H + h, j * KS, b);
+        mbar_arrive_expect_tx(&bar_vfull[st], TILE_V_BYTES);
+        tma_load_2d(smem + SMEM_V + st * TILE_V_BYTES, &vt_map, &bar_vfull[st], j * KS, vrow);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issue: the warp runs converged, one elected lane issues =====================
+    constexpr uint32_t idesc_s = umma_idesc_f16(QT, KS);   // 128 x 64 (keys)
+    constexpr uint32_t idesc_o = umma_idesc_f16(QT, DH);   // 128 x 64 (head dims)
+    const uint32_t q_addr = smem_u32(smem + SMEM_Q), k_addr = smem_u32(smem + SMEM_K), v_addr = smem_u32(smem + SMEM_V);
+    const uint32_t t_s = tmem_base + TMEM_S, t_o = tmem_base + TMEM_O;
+    const uint64_t dq = umma_desc_k_sw128(q_addr);
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T
+      const uint64_t dk = umma_desc_k_sw128(k_addr + (j % NS) * TILE_K_BYTES);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_f16_ss_elect(t_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    };
+    auto issue_o = [&](int j) {   // O += P_j V_j, P_j read from TMEM (64 F16 = 32 columns over the score buffer)
+      const uint64_t dv = umma_desc_k_sw128(v_addr + (j % NS) * TILE_V_BYTES);
+#pragma unroll
+      for (int k = 0; k < KS / 16; ++k) umma_f16_ts_elect(t_o, t_s + 8 * k, dv + 2 * k, idesc_o, (j | k) != 0);
+    };
+    mbar_wait(&bar_kfull[0], 0);
+    mbar_wait(bar_q, 0);
+    tc_fence_after();
+    issue_s(0);
+    umma_commit_elect(bar_s);
+    for (int j = 0; j < n_steps; ++j) {
+      const int st = j % NS;
+      mbar_wait(bar_p, j & 1);                          // P_j in TMEM, S_j consumed
+      mbar_wait(&bar_vfull[st], (j / NS) & 1);
+      tc_fence_after();
+      issue_o(j);
+      umma_commit_elect(&bar_free[st]);                 // K_j (read by S_j, retired earlier) and V_j are free once this retires
+      if (j == n_steps - 1) umma_commit_elect(bar_done);
+      if (j + 1 < n_steps) {
+        mbar_wait(&bar_kfull[(j + 1) % NS], ((j + 1) / NS) & 1);
+        tc_fence_after();
+        issue_s(j + 1);   // overwrites S_j / P_j: ordered behind the P.V MMAs above by the tensor pipe
+        umma_commit_elect(bar_s);
+      }
+    }
+  } else {
+    // ===================== softmax: thread r owns query row r (TMEM lane r) =====================
+    const int r = tid & (QT - 1);
+    const uint32_t trow = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t my_s = trow + TMEM_S, my_o = trow + TMEM_O;
+    const float c = a.scale_log2;
+    float m_used = -INFINITY;   // row max (raw score units) the exponent offset currently refers to
+    uint64_t l2 = f2_pack(0.0f, 0.0f);   // running denominator, two lanes
+
+    auto step = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const int kbase = j * KS;
+      mbar_wait(bar_s, j & 1);   // S_j ready; every earlier MMA (P_{j-1} V_{j-1}) has retired too: O is idle
+      __syncwarp();
+      tc_fence_after();
+      // ---- one TMEM pass: the row's 64 scores into registers (TMEM reads are 64 B/clk/SM: a second pass over
+      // the scores costs as much as the whole softmax)
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(my_s, s0);
+      tmem_ld_32x32b_x32(my_s + 32, s1);
+      tmem_ld_wait();
+      if (MASKED) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i >= T) s0[i] = 0xff800000u;   // -inf: masked key
+          if (kbase + 32 + i >= T) s1[i] = 0xff800000u;
+        }
+      }
+      const float mx = fmaxf(max_chunk4(s0), max_chunk4(s1));
+      // ---- lazy running max: rescale O and the denominator only when this row's max grew by more than 2^8
+      const bool grow = (mx - m_used) * c > RESCALE_LOG2;   // true on the first step (m_used = -inf)
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? exp2f((m_used - mx) * c) : 1.0f;
+        rescale_o4(my_o, alpha);
+        l2 = f2_fma(l2, f2_pack(alpha, alpha), f2_pack(0.0f, 0.0f));
+      }
+      if (grow) m_used = mx;
+      const float moff = m_used * c;
+      // ---- P = 2^(c s - m c) as F16 pairs over the first 32 columns of the score buffer just read
+      {
+        uint32_t p[16];
+        exp_chunk4(s0, c, moff, p, l2);
+        tmem_st_32x32b_x16(my_s, p);
+        exp_chunk4(s1, c, moff, p, l2);
+        tmem_st_32x32b_x16(my_s + 16, p);
+      }
+      tmem_st_wait();
+      tc_fence_before();   // TMEM accesses ordered before the MMAs the MMA warp issues
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_p);   // (128 arrivals on one barrier word serialise in the shared-memory atomic unit)
+    };
+#pragma unroll 1
+    for (int j = 0; j < n_steps - 1; ++j) step(j, BoolTagT<false>{});
+    if (n_steps * KS > T) step(n_steps - 1, BoolTagT<true>{});
+    else step(n_steps - 1, BoolTagT<false>{});
+    mbar_wait(bar_done, 0);
+    __syncwarp();
+    tc_fence_after();
+    // ---- normalise and store merged heads: out[(b*T + t)][h*64 + c]  (permute + cpy, 1924-1929)
+    float la, lb;
+    f2_unpack(l2, la, lb);
+    const float inv = 1.0f / (la + lb);
+    const int t = q0 + r;
+    __half* orow = a.out + ((long long)b * T + min(t, T - 1)) * (H * DH) + h * DH;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(my_o + half * 32, o);
+      tmem_ld_wait();
+      if (t < T) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + half * 32);
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          uint4 u;
+          u.x = pack_h2(__uint_as_float(o[8 * q8 + 0]) * inv, __uint_as_float(o[8 * q8 + 1]) * inv);
+          u.y = pack_h2(__uint_as_float(o[8 * q8 + 2]) * inv, __uint_as_float(o[8 * q8 + 3]) * inv);
+          u.z = pack_h2(__uint_as_float(o[8 * q8 + 4]) * inv, __uint_as_float(o[8 * q8 + 5]) * inv);
+          u.w = pack_h2(__uint_as_float(o[8 * q8 + 6]) * inv, __uint_as_float(o[8 * q8 + 7]) * inv);
+          dst[q8] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace
+
+bool attention4_setup_attributes(const char** err) {
+  cudaError_t e = cudaFuncSetAttribute(attention4_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ATTN4_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+// p.qk_map64: box {64, 1, 64, 1}; p.vt_map64: box {64, 64}
+cudaError_t launch_attention4(const AttnProblem& p, cudaStream_t st) {
+  Attn4Args a;
+  a.B = p.B;
+  a.T = p.T;
+  a.H = p.H;
+  a.n_steps = (p.T + KS - 1) / KS;
+  a.out = p.out;
+  a.scale_log2 = p.scale * 1.4426950408889634f;
+  dim3 grid((p.T + QT - 1) / QT, p.H, p.B);
+  return launch_pdl(attention4_tcgen05_kernel, grid, dim3(ATTN4_THREADS), ATTN4_SMEM_BYTES, st, p.qk_map64, p.vt_map64, a);
+}
+
+}  // namespace wb

@@ -7,6 +7,10 @@
 #include <string.h>
 
 #include <chrono>
+#include <thread>
+#if defined(__F16C__)
+#include <immintrin.h>
+#endif
 
 #include "wb_internal.hpp"
 
@@ -181,6 +185,16 @@ void resolve_kernel_clocks(wb_ctx* ctx) {
   it->second.clear();
 }
 
+// WB_ATTN4=1 (read at every call): the single-score-buffer attention kernel of attention4.cu (three CTAs per SM)
+// instead of attention.cu (two CTAs per SM, double-buffered scores).  Measured equal or slower; kept selectable.
+static bool use_attn4() {
+  const char* e = getenv("WB_ATTN4");
+  return e && e[0] == '1';
+}
+static cudaError_t run_attention(const AttnProblem& ap, cudaStream_t st) {
+  return (use_attn4() && ap.has_map64) ? launch_attention4(ap, st) : launch_attention(ap, st);
+}
+
 static bool force_gemm1() {
   static const bool v = getenv("WB_GEMM1") != nullptr;   // developer aid: A/B the single-CTA kernel
   return v;
@@ -351,6 +365,43 @@ int upload_cat(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPart>&
   return make_linear_maps(ctx, l, want_a_map) ? WB_OK : WB_ERR_TENSOR_OP;
 }
 
+// host F16 <-> f32 (round to nearest even): F16C when the host compiler has it, else cuda_fp16's software path
+static inline float h2f_host(uint16_t h) {
+#if defined(__F16C__)
+  return _cvtsh_ss(h);
+#else
+  __half v;
+  memcpy(&v, &h, 2);
+  return __half2float(v);
+#endif
+}
+static inline uint16_t f2h_host(float f) {
+#if defined(__F16C__)
+  return _cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+#else
+  const __half v = __float2half_rn(f);
+  uint16_t h;
+  memcpy(&h, &v, 2);
+  return h;
+#endif
+}
+template <class F>
+static void parallel_rows(int n, F&& body) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt < 2 || n < 64) {
+    body(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int per = (n + (int)nt - 1) / (int)nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const int lo = (int)t * per, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) th.emplace_back([&body, lo, hi] { body(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+
 // A Linear whose input is LayerNorm(x) (gamma, beta), with the LayerNorm's affine part and the part's output
 // scale s folded into it:  w = s * W diag(gamma) rounded to F16;  ln_c1[n] = sum_k w[n][k];
 // bias = c2[n] = s * (sum_k W[n][k] beta[k] + b[n]).  Then
@@ -381,19 +432,25 @@ int upload_cat_ln(wb_ctx* ctx, const ModelFileView& mv, const std::vector<CatPar
       if (!pbt) return fail_msg(ctx, WB_ERR_BAD_REF_TENSOR, "invalid ref tensor '" + p.b + "'\n");
       pb = reinterpret_cast<const float*>(pbt->data);
     }
-    for (int n = 0; n < N; ++n) {
-      double s1 = 0.0, s2 = 0.0;
-      __half* row = part.data() + (size_t)n * K;
-      for (int k = 0; k < K; ++k) {
-        const float w = __half2float(row[k]);
-        const __half wf = __float2half_rn(p.scale * w * g[k]);
-        row[k] = wf;
-        s1 += (double)__half2float(wf);
-        s2 += (double)w * (double)be[k];
+    const size_t c0 = c1.size();
+    c1.resize(c0 + N);
+    c2.resize(c0 + N);
+    // rows are independent: host threads, F16C conversions (a 3 GB model folds ~8e8 weights at load)
+    parallel_rows(N, [&](int n_lo, int n_hi) {
+      for (int n = n_lo; n < n_hi; ++n) {
+        double s1 = 0.0, s2 = 0.0;
+        uint16_t* row = reinterpret_cast<uint16_t*>(part.data()) + (size_t)n * K;
+        for (int k = 0; k < K; ++k) {
+          const float w = h2f_host(row[k]);
+          const uint16_t wf = f2h_host(p.scale * w * g[k]);
+          row[k] = wf;
+          s1 += (double)h2f_host(wf);
+          s2 += (double)w * (double)be[k];
+        }
+        c1[c0 + n] = (float)s1;
+        c2[c0 + n] = (float)((double)p.scale * (s2 + (pb ? (double)pb[n] : 0.0)));
       }
-      c1.push_back((float)s1);
-      c2.push_back((float)((double)p.scale * (s2 + (pb ? (double)pb[n] : 0.0))));
-    }
+    });
     h.insert(h.end(), part.begin(), part.end());
   }
   l.K = K;
@@ -608,7 +665,8 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
   const char* aerr = "";
-  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
+  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr) ||
+      !attention4_setup_attributes(&aerr)) {
     fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'kernel attribute setup: ") + aerr + "'");
     return bail(WB_ERR_TENSOR_OP);
   }
@@ -981,6 +1039,15 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     const uint64_t strd[1] = {(uint64_t)ctx->Tp * 2};
     const uint32_t box[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
     ok = make_tmap_f16(&ap.vt_map, ctx->vt, 2, dims, strd, box, &terr);
+    const uint32_t box64[2] = {64, 64};
+    ok = ok && make_tmap_f16(&ap.vt_map64, ctx->vt, 2, dims, strd, box64, &terr);
+  }
+  if (ok) {
+    const uint64_t dims[4] = {64, (uint64_t)2 * H, (uint64_t)T, (uint64_t)n_seg};
+    const uint64_t strd[3] = {128, (uint64_t)2 * d * 2, (uint64_t)T * 2 * d * 2};
+    const uint32_t box64[4] = {64, 1, 64, 1};
+    ok = make_tmap_f16(&ap.qk_map64, ctx->qk, 4, dims, strd, box64, &terr);
+    ap.has_map64 = ok;
   }
   // epilogue output / residual boxes of the pair GEMM
   CUtensorMap o_conv1, o_x3, o_pe, o_x, o_qk, o_hid, o_cross;
@@ -1070,7 +1137,7 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     }
     {   // E7: flash attention + head merge (1922-1929)
       LaunchTimer t(ctx, "attention");
-      WB_CK(launch_attention(ap, st));
+      WB_CK(run_attention(ap, st));
     }
     {   // E8: output projection + bias + residual (1936-1942), in place on the residual stream
       GemmEpilogue e;
@@ -1389,8 +1456,12 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
     const uint64_t dims2[2] = {(uint64_t)Tp, (uint64_t)n_seg * H * ATTN_VT_HEAD_ROWS};
     const uint64_t strd2[1] = {(uint64_t)Tp * 2};
     const uint32_t box2[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
+    const uint32_t box64[4] = {64, 1, 64, 1}, box264[2] = {64, 64};
+    ap.has_map64 = true;
     if (!make_tmap_f16(&ap.qk_map, dQK, 4, dims, strd, box, &terr) ||
-        !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr)) {
+        !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr) ||
+        !make_tmap_f16(&ap.qk_map64, dQK, 4, dims, strd, box64, &terr) ||
+        !make_tmap_f16(&ap.vt_map64, dVt, 2, dims2, strd2, box264, &terr)) {
       fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
       cleanup();
       return WB_ERR_TENSOR_OP;
@@ -1410,7 +1481,7 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
   }
   {
     LaunchTimer t(ctx, "dbg_attention");
-    DBG_CK(launch_attention(ap, ctx->stream));
+    DBG_CK(run_attention(ap, ctx->stream));
   }
   DBG_CK(cudaStreamSynchronize(ctx->stream));
   if (d_trace) {

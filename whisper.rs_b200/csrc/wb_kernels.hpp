@@ -106,12 +106,17 @@ constexpr int ATTN_VT_HEAD_ROWS = 80;   // 64 head rows + 1 row of ones + 15 zer
 struct AttnProblem {
   CUtensorMap qk_map;  // dims {64, 2H, T, B} over the [B*T][2d] Q|K buffer, box {64,1,128,1}
   CUtensorMap vt_map;  // dims {Tp, B*H*80} over V^T, box {64, 80}
+  CUtensorMap qk_map64;  // the same tensors with 64-row boxes ({64,1,64,1} / {64, 64}) for the 4-CTA-per-SM
+  CUtensorMap vt_map64;  // kernel (attention4.cu); valid when has_map64
+  bool has_map64 = false;
   int B = 0, T = 0, H = 0;
   __half* out = nullptr;  // [B*T][H*64] merged heads (1924-1929)
   float scale = 0.125f;
   long long* dbg = nullptr;  // optional clock64() trace buffer (1024 entries) for tools/prof_attention.py
 };
 cudaError_t launch_attention(const AttnProblem& a, cudaStream_t st);
+cudaError_t launch_attention4(const AttnProblem& a, cudaStream_t st);   // attention4.cu: four CTAs per SM
+bool attention4_setup_attributes(const char** err);
 cudaError_t launch_vt_init(__half* vt, int n_heads_total, int Tp, cudaStream_t st);   // ones / zero rows
 bool attention_setup_attributes(const char** err);
 
