@@ -85,10 +85,19 @@ struct AttnArgs {
   float scale_log2;   // scale * log2(e)
   long long* dbg;     // optional: clock64() trace of CTA (0,0,0) (tools/attn_trace.py); nullptr in production
 };
+// clock64() trace points: compiled in only with -DWB_ATTN_TRACE_BUILD (tools/attn_trace.py); as run-time
+// predicated code they cost ~15 issue slots per softmax step
+#ifdef WB_ATTN_TRACE_BUILD
 #define ATTN_TRACE(slot)                                                          \
   do {                                                                            \
     if (trace) a.dbg[(slot)] = clock64();                                         \
   } while (0)
+#else
+#define ATTN_TRACE(slot) \
+  do {                   \
+    (void)trace;         \
+  } while (0)
+#endif
 
 template <bool B>
 struct BoolTag {
@@ -116,15 +125,15 @@ __device__ __noinline__ void rescale_o(uint32_t taddr_o, float alpha) {
 // The scale-and-offset runs as packed FFMA2 (two keys per instruction); of every 16 key PAIRS, those
 // whose bit is set in POLY_PAIR_MASK evaluate both exponentials on the FMA pipe (packed cubic), the
 // rest go through the MUFU unit.
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float moff, uint32_t (&p)[16]) {
-  const uint64_t c2 = f2_pack(c, c), m2 = f2_pack(-moff, -moff);
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint64_t c2, uint64_t m2, uint32_t (&p)[16],
+                                          const Ex2Consts& K) {
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), c2, m2);
     float x0, x1, e0, e1;
     f2_unpack(x2, x0, x1);
     if ((POLY_PAIR_MASK >> u) & 1u) {
-      ex2_fma_x2(x0, x1, e0, e1);
+      ex2_fma_x2(x0, x1, e0, e1, K);
     } else {
       e0 = ex2_mufu(x0);
       e1 = ex2_mufu(x1);
@@ -276,6 +285,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     const float c = a.scale_log2;
     float m_used = -INFINITY;   // row max (raw score units) the exponent offset currently refers to
     const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0;
+    Ex2Consts K;
+    K.load();
+    uint64_t c2;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(c));
 
     // one 64-key step.  MASKED = the last step of the sequence (keys >= T get -inf); kept out of the
     // steady-state instantiation: as a run-time test the compiler turns it into 3 predicated
@@ -320,9 +333,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
       // buffer just read
       {
         uint32_t p[16];
-        exp_chunk(s0, c, moff, p);
+        const uint64_t m2 = f2_pack(-moff, -moff);
+        exp_chunk(s0, c2, m2, p, K);
         tmem_st_32x32b_x16(my_s, p);
-        exp_chunk(s1, c, moff, p);
+        exp_chunk(s1, c2, m2, p, K);
         tmem_st_32x32b_x16(my_s + 16, p);
       }
       tmem_st_wait();

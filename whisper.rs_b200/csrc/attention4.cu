@@ -77,15 +77,15 @@ __device__ __noinline__ void rescale_o4(uint32_t taddr_o, float alpha) {
 
 // P for 32 keys: 2^(c s - m c) as F16 pairs (register u = keys 2u, 2u + 1); the f32 values are also added
 // into the two-lane running denominator
-__device__ __forceinline__ void exp_chunk4(const uint32_t (&s)[32], float c, float moff, uint32_t (&p)[16], uint64_t& l2) {
-  const uint64_t c2 = f2_pack(c, c), m2 = f2_pack(-moff, -moff);
+__device__ __forceinline__ void exp_chunk4(const uint32_t (&s)[32], uint64_t c2, uint64_t m2, uint32_t (&p)[16], uint64_t& l2,
+                                           const Ex2Consts& K) {
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), c2, m2);
     float x0, x1, e0, e1;
     f2_unpack(x2, x0, x1);
     if ((POLY_PAIR_MASK >> u) & 1u) {
-      ex2_fma_x2(x0, x1, e0, e1);
+      ex2_fma_x2(x0, x1, e0, e1, K);
     } else {
       e0 = ex2_mufu(x0);
       e1 = ex2_mufu(x1);
@@ -211,6 +211,10 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gr
     const float c = a.scale_log2;
     float m_used = -INFINITY;   // row max (raw score units) the exponent offset currently refers to
     uint64_t l2 = f2_pack(0.0f, 0.0f);   // running denominator, two lanes
+    Ex2Consts K;
+    K.load();
+    uint64_t c2;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(c));
 
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
@@ -244,9 +248,10 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gr
       // ---- P = 2^(c s - m c) as F16 pairs over the first 32 columns of the score buffer just read
       {
         uint32_t p[16];
-        exp_chunk4(s0, c, moff, p, l2);
+        const uint64_t m2 = f2_pack(-moff, -moff);
+        exp_chunk4(s0, c2, m2, p, l2, K);
         tmem_st_32x32b_x16(my_s, p);
-        exp_chunk4(s1, c, moff, p, l2);
+        exp_chunk4(s1, c2, m2, p, l2, K);
         tmem_st_32x32b_x16(my_s + 16, p);
       }
       tmem_st_wait();

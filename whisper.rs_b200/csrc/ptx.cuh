@@ -384,15 +384,27 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
   return r;
 }
 // ex2_fma for two values at once: the magic-number split, the cubic and its Horner steps are packed
-// (7 issue slots + 2 clamps + 2 exponent IMADs for the pair, against 16 for two scalar evaluations)
-__device__ __forceinline__ void ex2_fma_x2(float x0, float x1, float& e0, float& e1) {
+// (7 issue slots + 2 clamps + 2 exponent IMADs for the pair, against 16 for two scalar evaluations).
+// The five packed constants live in registers the caller loads ONCE (Ex2Consts::load, an opaque asm the
+// compiler cannot rematerialise): left to itself ptxas rebuilds each 64-bit constant with two moves per use,
+// ~30 issue slots per 64-key softmax step.
+struct Ex2Consts {
+  uint64_t magic, k3, k2, k1, k0;
+  __device__ __forceinline__ void load() {
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(magic) : "f"(12582912.0f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(k3) : "f"(0.0551716648f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(k2) : "f"(0.2426111251f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(k1) : "f"(0.6932609677f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(k0) : "f"(0.9999280572f));
+  }
+};
+__device__ __forceinline__ void ex2_fma_x2(float x0, float x1, float& e0, float& e1, const Ex2Consts& K) {
   const uint64_t x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
-  const uint64_t t = f2_add(x, magic);
-  const uint64_t f = f2_sub(x, f2_sub(t, magic));
-  uint64_t p = f2_fma(f, f2_pack(0.0551716648f, 0.0551716648f), f2_pack(0.2426111251f, 0.2426111251f));
-  p = f2_fma(p, f, f2_pack(0.6932609677f, 0.6932609677f));
-  p = f2_fma(p, f, f2_pack(0.9999280572f, 0.9999280572f));
+  const uint64_t t = f2_add(x, K.magic);
+  const uint64_t f = f2_sub(x, f2_sub(t, K.magic));
+  uint64_t p = f2_fma(f, K.k3, K.k2);
+  p = f2_fma(p, f, K.k1);
+  p = f2_fma(p, f, K.k0);
   float t0, t1, p0, p1;
   f2_unpack(t, t0, t1);
   f2_unpack(p, p0, p1);

@@ -606,6 +606,12 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   if (!model_path || !out) return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: null argument");
   *out = nullptr;
   const auto t_start = std::chrono::steady_clock::now();
+  const bool load_trace = getenv("WB_LOAD_TRACE") != nullptr;   // developer aid: where context creation spends its time
+  auto trace = [&](const char* what) {
+    if (load_trace)
+      fprintf(stderr, "[libwhisper_b200] load %-24s %8.3f s\n", what,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+  };
   wb_config cfg;
   if (cfg_in) cfg = *cfg_in;
   else wb_config_default(&cfg);
@@ -616,6 +622,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   std::string perr;
   int rc = parse_model_file(model_path, mv, perr);
   if (rc != WB_OK) return fail_msg(nullptr, rc, perr);
+  trace("file parsed");
   const ModelHParams& hp = mv.hp;
   if (hp.n_audio_state / hp.n_audio_head != 64 || hp.n_text_state / hp.n_text_head != 64)
     return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: head dimension must be 64");
@@ -677,6 +684,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     rc = (x);             \
     if (rc) return bail(rc); \
   } while (0)
+  trace("device + stream ready");
   TRY(build_mel_tables(ctx, mv));
   {
     // LayerNorm folded into the GEMMs around it (default; WB_LN_FOLD=0 keeps the separate LayerNorm kernel):
@@ -724,8 +732,11 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     }
     if (!parts.empty()) TRY(upload_cat(ctx, mv, parts, ctx->cross_kv, false));
   }
+  trace("encoder weights");
   TRY(alloc_activations(ctx));
-  if (cfg.decode_capacity) TRY(decode_setup(ctx, mv));   // decoder weights + KV cache (wb_decode.cu)
+  trace("activations");
+  if (cfg.decode_capacity) TRY(decode_setup(ctx, mv));
+  trace("decoder weights + state");   // decoder weights + KV cache (wb_decode.cu)
 #undef TRY
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
     fail(ctx, WB_ERR_TENSOR_OP, "weight upload", e);
