@@ -294,7 +294,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     // steady-state instantiation: as a run-time test the compiler turns it into 3 predicated
     // instructions per element on every step.
     // (Tried and measured slower or equal on B200, see DESIGN.md: 16 softmax warps with half a row per
-    // thread; software-pipelining the next step's TMEM load and max under the exponentials.)
+    // thread; software-pipelining the next step's TMEM load and max under the exponentials; requesting the
+    // next step's scores into each half of the score registers as soon as its exponentials are done -- no
+    // extra registers, but 579 -> 525 TFLOP/s: the barrier wait + fence + tcgen05.ld in mid-step stall the
+    // exponential stream more than the early data saves.)
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int sb = j & 1;
