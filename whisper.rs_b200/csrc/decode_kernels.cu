@@ -212,44 +212,55 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
 //   q   [n_seq*n_tok][d] F16 (already scaled by Dh^-1/4)
 //   K/V rows: kv[(seq*T + t)*ld + h*64 ..], K at `k`, V at `v` (same row pitch)
 // grid (H, n_seq, n_split): each CTA handles keys [split*span, ...) for every query token; with
-// n_split > 1 it emits (max, sum, unnormalised o) partials that cross_combine_kernel merges.
+// n_split > 1 it emits (max, sum, o normalised within the split) partials; the CTA of a (row, head) that
+// finishes last merges them.
 constexpr int CROSS_THREADS = 256;
 constexpr int CROSS_MAX_SPAN = 1536;
-constexpr int CROSS_U = 8;
+constexpr int CROSS_U = 4;          // K rows AND V rows per lane requested together (8 x 16 bytes in flight per lane)
+constexpr int CROSS_GROUPS = (CROSS_THREADS / 32) * 4;   // 8-lane groups per CTA: one key row each per instruction
 
+// One pass over the keys (online softmax): every 8-lane group walks its rows with K and V requested together
+// and keeps a running (max, denominator, 8 output dims per lane); the 32 groups are merged once at the end.
+// Against two passes (scores -> shared memory, block softmax, then V) there is no mid-kernel barrier during
+// which all resident CTAs stop streaming at the same time, and twice the loads are in flight in steady state.
+// The probabilities are rounded to F16 before P.V as in the reference, relative to the running maximum.
 __global__ void __launch_bounds__(CROSS_THREADS, 3)
 decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
                          long long ld, long long head_stride, int n_tok, int T, int span, __half* __restrict__ out,
-                         float* __restrict__ part_o, float* __restrict__ part_ml, int n_split) {
-  __shared__ float sc[CROSS_MAX_SPAN];
-  __shared__ float red[CROSS_THREADS / 32];
-  __shared__ float opart[CROSS_THREADS / 32][4][DH];
+                         float* __restrict__ part_o, float* __restrict__ part_ml, int n_split, int* __restrict__ split_cnt) {
+  __shared__ float g_m[CROSS_GROUPS], g_l[CROSS_GROUPS];
+  __shared__ int s_last;
+  __shared__ float g_o[CROSS_GROUPS][DH];
   const int h = blockIdx.x, s = blockIdx.y, sp = blockIdx.z, H = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane >> 3, ch = lane & 7;
   const int t_lo = sp * span, t_hi = min(T, t_lo + span), n = t_hi - t_lo;
   const __half* kb = k + ((size_t)s * T + t_lo) * ld + h * head_stride + ch * 8;
   const __half* vb = v + ((size_t)s * T + t_lo) * ld + h * head_stride + ch * 8;
-  // The encoder memory does not depend on the previous kernel of the step (only q does): this CTA's K rows
-  // (one 128-byte line each) are requested into L2 before the grid dependency resolves, i.e. under the
-  // latency-bound linear layer in front.
   pdl_launch_dependents();
-  for (int t = tid; t < n; t += CROSS_THREADS) prefetch_l2(k + ((size_t)s * T + t_lo + t) * ld + h * head_stride);
-  pdl_wait();
+  pdl_wait();   // q is the previous kernel's output
+  constexpr int RPI = CROSS_GROUPS;   // rows per CTA iteration
   for (int i = 0; i < n_tok; ++i) {
     const int row = s * n_tok + i;
     float qf[8];
     unpack8(*reinterpret_cast<const uint4*>(q + (size_t)row * d + h * DH + ch * 8), qf);
-    // CROSS_U independent 16-byte loads in flight per lane: with all 384 CTAs resident that is ~12 MB in flight,
-    // what HBM latency x bandwidth asks for (4 per lane measured 4.5 TB/s)
-    constexpr int RPI = (CROSS_THREADS / 32) * 4;   // rows per CTA iteration
+    float m = -INFINITY, l = 0.0f, o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
     for (int t0 = warp * 4; t0 < n; t0 += CROSS_U * RPI) {
-      uint4 kv[CROSS_U];
+      uint4 kv[CROSS_U], vv[CROSS_U];
 #pragma unroll
       for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
         kv[u] = t < n ? ld_nc_v4(kb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
       }
+#pragma unroll
+      for (int u = 0; u < CROSS_U; ++u) {
+        const int t = t0 + u * RPI + sub;
+        vv[u] = t < n ? ld_nc_v4(vb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float sc[CROSS_U];
+      float bm = -INFINITY;
 #pragma unroll
       for (int u = 0; u < CROSS_U; ++u) {
         const int t = t0 + u * RPI + sub;
@@ -261,52 +272,48 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ch == 0 && t < n) sc[t] = acc;
+        sc[u] = t < n ? acc : -INFINITY;
+        bm = fmaxf(bm, sc[u]);
       }
-    }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int t = tid; t < n; t += CROSS_THREADS) mx = fmaxf(mx, sc[t]);
-    mx = block_max(mx, red, CROSS_THREADS / 32);
-    float sum = 0.0f;
-    for (int t = tid; t < n; t += CROSS_THREADS) {
-      const float e = __expf(sc[t] - mx);
-      sc[t] = e;
-      sum += e;
-    }
-    sum = block_sum(sum, red, CROSS_THREADS / 32);
-    const float inv = 1.0f / sum;
-    float o[8];
+      const float m_new = fmaxf(m, bm);
+      if (m_new > -INFINITY) {   // (group-uniform: the 8 lanes hold the same scores)
+        const float alpha = __expf(m - m_new);   // 0 on the group's first rows (m = -inf)
+        l *= alpha;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < n; t0 += CROSS_U * RPI) {
-      uint4 vv[CROSS_U];
+        for (int j = 0; j < 8; ++j) o[j] *= alpha;
 #pragma unroll
-      for (int u = 0; u < CROSS_U; ++u) {
-        const int t = t0 + u * RPI + sub;
-        vv[u] = t < n ? ld_nc_v4(vb + (size_t)t * ld) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < CROSS_U; ++u) {
-        const int t = t0 + u * RPI + sub;
-        if (t < n) {
-          const float p = __half2float(__float2half_rn(sc[t] * inv));   // P -> F16 before P.V
+        for (int u = 0; u < CROSS_U; ++u) {
+          const float e = __expf(sc[u] - m_new);   // 0 for a row past the end
+          l += e;
+          const float p = __half2float(__float2half_rn(e));   // P -> F16 before P.V
           float vf[8];
           unpack8(vv[u], vf);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
         }
+        m = m_new;
       }
     }
+    const int grp = warp * 4 + sub;
+    if (ch == 0) {
+      g_m[grp] = m;
+      g_l[grp] = l;
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) opart[warp][sub][ch * 8 + j] = o[j];
+    for (int j = 0; j < 8; ++j) g_o[grp][ch * 8 + j] = o[j];
     __syncthreads();
     if (tid < DH) {
-      float r = 0.0f;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < CROSS_THREADS / 32; ++w)
+      for (int gq = 0; gq < CROSS_GROUPS; ++gq) mx = fmaxf(mx, g_m[gq]);
+      float sum = 0.0f, r = 0.0f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) r += opart[w][u][tid];
+      for (int gq = 0; gq < CROSS_GROUPS; ++gq) {
+        const float w = g_m[gq] > -INFINITY ? __expf(g_m[gq] - mx) : 0.0f;
+        sum = fmaf(w, g_l[gq], sum);
+        r = fmaf(w, g_o[gq][tid], r);
+      }
+      r = sum > 0.0f ? r / sum : 0.0f;
       if (n_split == 1) {
         out[(size_t)row * d + h * DH + tid] = __float2half_rn(r);
       } else {
@@ -318,26 +325,36 @@ decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __re
         }
       }
     }
+    if (n_split > 1) {
+      // the key range of a (row, head) is split over n_split CTAs so that 148 SMs x 3 resident CTAs stay evenly
+      // loaded (384 whole items leave SMs with 2 or 3 of them: 86 %); the CTA that finishes last merges the
+      // partials -- no second launch
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int old = atomicAdd(&split_cnt[row * H + h], 1);
+        s_last = old == n_split - 1;
+        if (s_last) split_cnt[row * H + h] = 0;   // ready for the next launch
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (tid < DH) {
+          const size_t p0 = ((size_t)row * H + h) * n_split;
+          float mm = -INFINITY;
+          for (int q2 = 0; q2 < n_split; ++q2) mm = fmaxf(mm, __ldcg(part_ml + (p0 + q2) * 2));
+          float den = 0.0f, acc = 0.0f;
+          for (int q2 = 0; q2 < n_split; ++q2) {
+            const float w = __ldcg(part_ml + (p0 + q2) * 2 + 1) * __expf(__ldcg(part_ml + (p0 + q2) * 2) - mm);
+            den += w;
+            acc = fmaf(w, __ldcg(part_o + (p0 + q2) * DH + tid), acc);
+          }
+          out[(size_t)row * d + h * DH + tid] = __float2half_rn(acc / den);
+        }
+      }
+    }
     __syncthreads();
   }
-}
-
-// merge split partials: out = sum_s w_s o_s, w_s = l_s e^(m_s - m) / sum_s' l_s' e^(m_s' - m)
-__global__ void cross_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int n_split,
-                                     int d, __half* __restrict__ out) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
-  const int h = blockIdx.x, row = blockIdx.y, H = gridDim.x, c = threadIdx.x;
-  const size_t p0 = ((size_t)row * H + h) * n_split;
-  float m = -INFINITY;
-  for (int s = 0; s < n_split; ++s) m = fmaxf(m, part_ml[(p0 + s) * 2]);
-  float den = 0.0f, acc = 0.0f;
-  for (int s = 0; s < n_split; ++s) {
-    const float w = part_ml[(p0 + s) * 2 + 1] * __expf(part_ml[(p0 + s) * 2] - m);
-    den += w;
-    acc = fmaf(w, part_o[(p0 + s) * DH + c], acc);
-  }
-  out[(size_t)row * d + h * DH + c] = __float2half_rn(acc / den);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -755,6 +772,9 @@ cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half
                     n_text_ctx, out);
 }
 
+// key-range splits per (sequence, head): only when there are too few (sequence, head) pairs to fill the SMs.
+// (Splitting to even out 384 pairs over 148 SMs x 3 resident CTAs -- 86 % balanced -- was measured: four splits
+// of 375 keys run 360 -> 480 us per step; a CTA needs the long key range to keep its loads in flight.)
 int decode_cross_splits(int n_seq, int H, int T, int num_sms) {
   int n_split = 1;
   while (n_seq * H * n_split < 2 * num_sms && n_split < 8 && (T + n_split * 2 - 1) / (n_split * 2) >= 128) n_split *= 2;
@@ -763,13 +783,11 @@ int decode_cross_splits(int n_seq, int H, int T, int num_sms) {
 
 cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, const __half* v, long long ld_kv,
                                      long long head_stride, int n_seq, int n_tok, int T, int H, __half* out,
-                                     float* part_o, float* part_ml, int n_split, cudaStream_t st) {
+                                     float* part_o, float* part_ml, int n_split, int* split_cnt, cudaStream_t st) {
   const int span = (T + n_split - 1) / n_split;
   if (span > CROSS_MAX_SPAN) return cudaErrorInvalidValue;
-  cudaError_t e = launch_pdl(decode_cross_attn_kernel, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
-                             head_stride, n_tok, T, span, out, part_o, part_ml, n_split);
-  if (e != cudaSuccess || n_split == 1) return e;
-  return launch_pdl(cross_combine_kernel, dim3(H, n_seq * n_tok), dim3(DH), 0, st, part_o, part_ml, n_split, d, out);
+  return launch_pdl(decode_cross_attn_kernel, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
+                    head_stride, n_tok, T, span, out, part_o, part_ml, n_split, split_cnt);
 }
 
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,

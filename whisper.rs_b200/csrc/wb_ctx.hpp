@@ -133,6 +133,7 @@ struct wb_ctx {
   int *d_npast = nullptr, *d_step = nullptr;
   float *d_margin = nullptr, *d_out_margin = nullptr;
   float *d_part_o = nullptr, *d_part_ml = nullptr;
+  int* d_split_cnt = nullptr;                    // per (row, head) arrival counter of the split cross-attention
   int dec_n_seq = 0;
   const float *d_ones = nullptr, *d_zeros = nullptr;   // identity affine for the prompt pass's plain LayerNorm
   float2* dec_ln_stats = nullptr;                // [3 Lt + 1][DEC_LN_ROWS] row statistics of the folded single-token step

@@ -173,6 +173,7 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
   const size_t prow = (size_t)S * 8 * hp.n_text_head * 8;
   if ((rc = dev_alloc(ctx, &ctx->d_part_o, prow * 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_part_ml, prow * 2))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_split_cnt, (size_t)S * 8 * hp.n_text_head))) return rc;   // zeroed; self-resetting
   if ((rc = make_act_maps(ctx, ctx->m_ln, ctx->d_ln, d, (int)R))) return rc;
   if ((rc = make_act_maps(ctx, ctx->m_att, ctx->d_att, d, (int)R))) return rc;
   if ((rc = make_act_maps(ctx, ctx->m_hid, ctx->d_hid, 4 * d, (int)R))) return rc;
@@ -264,7 +265,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
       const bool hm = dec_skip("headmajor");
       WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + ctx->cross_slab, hm ? 64 : ld_kv,
                                      hm ? (long long)ctx->cfg.max_segments * T * 64 : 64, n_seq, n_tok, T, H, ctx->d_att,
-                                     ctx->d_part_o, ctx->d_part_ml, n_split, st));
+                                     ctx->d_part_o, ctx->d_part_ml, n_split, ctx->d_split_cnt, st));
     }
     {
       GemmEpilogue e;

@@ -167,7 +167,7 @@ cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half
 int decode_cross_splits(int n_seq, int H, int T, int num_sms);
 cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, const __half* v, long long ld_kv,
                                      long long head_stride, int n_seq, int n_tok, int T, int H, __half* out,
-                                     float* part_o, float* part_ml, int n_split, cudaStream_t st);
+                                     float* part_o, float* part_ml, int n_split, int* split_cnt, cudaStream_t st);
 // D6 / K13: per-sequence arg-max + top-2 margin + greedy-loop bookkeeping
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
                           float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
