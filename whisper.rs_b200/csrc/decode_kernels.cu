@@ -803,6 +803,9 @@ cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st) {
   const dim3 grid((a.N + DL_ROWS - 1) / DL_ROWS);
 #define WB_DL(U, NW) \
   if (a.K % (32 * (U) * (NW)) == 0 || ((U) == 4 && (NW) == 4)) return launch_pdl(decode_linear_kernel<U, NW>, grid, dim3(32 * (NW)), 0, st, a)
+  // many CTAs (the vocabulary projection: 3242 of them): waves x per-CTA latency sets the time, so the variant
+  // with the fewest registers (most resident CTAs) wins over the one with every load in flight
+  if ((int)grid.x > 16 * 148 && a.K % 256 == 0) WB_DL(2, 4);
   if (a.K <= 768) {          // 4 warps, every k-block of the CTA in flight at once when K = 128 U
     if (a.K == 768) WB_DL(6, 4);
     if (a.K == 640) WB_DL(5, 4);
