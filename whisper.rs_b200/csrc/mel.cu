@@ -241,16 +241,14 @@ float mel_dec_ordered_host(int i) {
 cudaError_t launch_mel_frames(const MelTables& t, const void* pcm, int pcm_is_i16, size_t n_samples, int n_clips,
                               int n_len, float* mel_out, int* clip_max_enc, cudaStream_t st) {
   if (n_len <= 0 || n_clips <= 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // opt-in to > 48 KB of dynamic shared memory, once (thread-safe function-local static)
+  static const cudaError_t attr_err = [] {
     cudaError_t e = cudaFuncSetAttribute(mel_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(MelSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mel_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(MelSmem));
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+    return cudaFuncSetAttribute(mel_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem));
+  }();
+  if (attr_err != cudaSuccess) return attr_err;
   dim3 grid((n_len + F - 1) / F, n_clips);
   if (pcm_is_i16)
     mel_frames_kernel<true><<<grid, MEL_THREADS, sizeof(MelSmem), st>>>(t, pcm, n_samples, n_len, mel_out, clip_max_enc);

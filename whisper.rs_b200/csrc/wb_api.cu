@@ -137,15 +137,9 @@ bool make_linear_maps(wb_ctx* ctx, Linear& l, bool want_a_map) {
 
 // ------------------------------------------------------------------------------------------------
 // kernel-family timing
-struct PendingEvent {
-  const char* fam;
-  cudaEvent_t a, b;
-};
-static std::unordered_map<wb_ctx*, std::vector<PendingEvent>> g_pending;
-static std::unordered_map<wb_ctx*, std::vector<cudaEvent_t>> g_free_events;
-
+// (the event lists live in the handle: two handles driven from two threads share no mutable state)
 static cudaEvent_t get_event(wb_ctx* c) {
-  auto& pool = g_free_events[c];
+  auto& pool = c->free_events;
   if (!pool.empty()) {
     cudaEvent_t e = pool.back();
     pool.pop_back();
@@ -166,23 +160,21 @@ LaunchTimer::LaunchTimer(wb_ctx* ctx, const char* family) : c(ctx), fam(family) 
 LaunchTimer::~LaunchTimer() {
   if (a) {
     cudaEventRecord(b, c->stream);
-    g_pending[c].push_back(PendingEvent{fam, a, b});
+    c->pending_events.push_back(PendingEvent{fam, a, b});
   }
 }
 void resolve_kernel_clocks(wb_ctx* ctx) {
-  auto it = g_pending.find(ctx);
-  if (it == g_pending.end()) return;
-  for (auto& pe : it->second) {
+  for (auto& pe : ctx->pending_events) {
     float ms = 0.0f;
     if (cudaEventSynchronize(pe.b) == cudaSuccess && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
       KernelClock& k = ctx->clocks[pe.fam];
       k.total_us += (double)ms * 1000.0;
       k.launches += 1;
     }
-    g_free_events[ctx].push_back(pe.a);
-    g_free_events[ctx].push_back(pe.b);
+    ctx->free_events.push_back(pe.a);
+    ctx->free_events.push_back(pe.b);
   }
-  it->second.clear();
+  ctx->pending_events.clear();
 }
 
 // WB_ATTN4=1 (read at every call): the single-score-buffer attention kernel of attention4.cu (three CTAs per SM)
@@ -753,9 +745,8 @@ void wb_ctx_free(wb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   resolve_kernel_clocks(ctx);
-  for (cudaEvent_t e : wb::g_free_events[ctx]) cudaEventDestroy(e);
-  wb::g_free_events.erase(ctx);
-  wb::g_pending.erase(ctx);
+  for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  ctx->free_events.clear();
   if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
   for (void* p : ctx->allocs) cudaFree(p);
   for (int i = 0; i < 3; ++i)

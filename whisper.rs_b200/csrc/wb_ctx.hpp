@@ -41,6 +41,11 @@ struct ActMaps {          // one activation buffer as the skinny GEMM operand, p
   CUtensorMap m[4];       // box {64, 32|64|128|256}
 };
 
+struct PendingEvent {   // one bracketed launch whose events have not been read yet
+  const char* fam;
+  cudaEvent_t a, b;
+};
+
 struct KernelClock {   // device time per kernel family (CUDA events on the handle's stream)
   double total_us = 0;
   int64_t launches = 0;
@@ -149,5 +154,7 @@ struct wb_ctx {
   bool ev_used[3] = {false, false, false};
   wb_timings tm{};
   std::unordered_map<std::string, wb::KernelClock> clocks;
+  std::vector<wb::PendingEvent> pending_events;
+  std::vector<cudaEvent_t> free_events;
   bool time_kernels = false;
 };
