@@ -118,3 +118,24 @@ def test_async_digest_tickets(pkg, model_path):
         api.wait(ctx, tickets[i])
         assert np.array_equal(out[i].numpy(), want[i]), i
     ctx.close()
+
+
+def test_assemble_segments(pkg, model_path):
+    """result_all / WhisperSegment (src/main.rs:354, 599-604): window times in centiseconds, text through id_to_token,
+    time-stamp tokens (id >= token_beg, 568) moving the clock inside their window."""
+    from whisper_rs_b200 import api, pipeline
+    ctx = api.WhisperContext.new(model_path("tiny.ml"), max_segments=1, max_clips=1, max_clip_samples=480000)
+    fpw = 2 * ctx.n_audio_ctx
+    beg = ctx.token_beg
+    toks = np.array([[beg, 11, 12, beg + 50, 13, beg + 100, 0, 0],
+                     [21, 22, 23, 24, 25, 26, 27, 28]], dtype=np.int32)
+    lens = np.array([6, 8], dtype=np.int32)
+    segs = pipeline.assemble_segments(ctx, [0, 2], toks, lens, None, n_samples=2 * fpw * 160 + 40 * 160)
+    assert [(s.t0, s.t1) for s in segs] == [(0, fpw), (2 * fpw, 2 * fpw + 40)]       # second window clipped to the clip
+    assert segs[0].text == ctx.tokens_to_text([11, 12, 13]) and segs[1].text == ctx.tokens_to_text(list(range(21, 29)))
+    t = segs[0].tokens
+    assert [x.id for x in t] == [beg, 11, 12, beg + 50, 13, beg + 100]
+    assert (t[0].t0, t[1].t0, t[3].t0, t[4].t0, t[5].t0) == (0, 0, 100, 100, 200)      # 2 cs per time-stamp step
+    assert t[1].tid == beg and t[4].tid == beg + 50
+    assert all(x.t0 >= segs[1].t0 for x in segs[1].tokens) and len(segs[1].tokens) == 8
+    ctx.close()

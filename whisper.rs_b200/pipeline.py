@@ -87,6 +87,54 @@ def transcribe_clip(ctx: api.WhisperContext, pcm: np.ndarray, *, rank: int = 0, 
     return part.windows, toks, lens, marg
 
 
+class WhisperTokenData:
+    """WhisperTokenData (src/main.rs:317-331): id, the time-stamp token it implies (tid), and the window-relative
+    times a time-stamp id carries (t0 / t1 in units of 10 ms, as upstream: id - token_beg steps of 20 ms).  The
+    probabilities of the reference's struct (p, pt, ptsum) belong to its sampling code, which it never implemented;
+    the greedy loop here reports the top-1 logit margin instead."""
+
+    __slots__ = ("id", "tid", "margin", "t0", "t1")
+
+    def __init__(self, id: int, tid: int, margin: float, t0: int, t1: int):
+        self.id, self.tid, self.margin, self.t0, self.t1 = id, tid, margin, t0, t1
+
+
+class WhisperSegment:
+    """WhisperSegment (src/main.rs:599-604): [t0, t1) in units of 10 ms from the start of the clip, the text of the
+    window's text tokens, and the tokens themselves."""
+
+    __slots__ = ("t0", "t1", "text", "tokens")
+
+    def __init__(self, t0: int, t1: int, text: bytes, tokens: List[WhisperTokenData]):
+        self.t0, self.t1, self.text, self.tokens = t0, t1, text, tokens
+
+
+def assemble_segments(ctx: api.WhisperContext, windows: Sequence[int], toks: np.ndarray, lens: np.ndarray,
+                      margins: Optional[np.ndarray] = None, n_samples: Optional[int] = None) -> List[WhisperSegment]:
+    """result_all (src/main.rs:354): one WhisperSegment per decoded 30 s window.  Window w covers
+    [3000 w, 3000 (w + 1)) centiseconds (clipped to the clip's length when `n_samples` is given); a time-stamp token
+    (id >= token_beg, 568) carries (id - token_beg) * 2 centiseconds relative to its window and ends the run of text
+    tokens before it; text = the window's text tokens (ids below eot) through id_to_token (544)."""
+    fpw = 2 * ctx.n_audio_ctx
+    out: List[WhisperSegment] = []
+    for i, w in enumerate(windows):
+        n = int(lens[i])
+        ids = [int(x) for x in toks[i][:n]]
+        w0 = w * fpw                                       # centiseconds: one mel frame = 10 ms
+        w1 = (w + 1) * fpw if n_samples is None else min((w + 1) * fpw, n_samples // HOP)
+        tdata: List[WhisperTokenData] = []
+        t_cur = w0
+        for k, tok in enumerate(ids):
+            m = float(margins[i][k]) if margins is not None else 0.0
+            if tok >= ctx.token_beg:                       # time-stamp token: moves the clock
+                t_cur = min(w0 + (tok - ctx.token_beg) * 2, w1)
+                tdata.append(WhisperTokenData(tok, tok, m, t_cur, t_cur))
+            else:
+                tdata.append(WhisperTokenData(tok, ctx.token_beg + (t_cur - w0) // 2, m, t_cur, w1))
+        out.append(WhisperSegment(w0, w1, ctx.tokens_to_text(ids), tdata))
+    return out
+
+
 def torch_reduce_max(device=None) -> Callable[[float], float]:
     """MAX all-reduce of one f32 over the default torch.distributed group (NCCL on `device`, gloo on CPU)."""
     import torch
