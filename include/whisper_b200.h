@@ -115,6 +115,10 @@ int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clip
  * reproduces the reference's call (2074).  Leaves ln_post output and the per-layer cross-attention
  * K/V (memory_cross_k/v, 1990-2030) on the device. */
 int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, int n_segments);
+/* exp_n_audio_ctx (362, read at 1803-1807): n_ctx > 0 makes the following wb_encode calls run with an audio context
+ * of n_ctx <= n_audio_ctx positions (a window of 2 * n_ctx mel frames, the first n_ctx rows of the positional
+ * embedding); 0 = the model's.  Read-backs, digests and the decoder's cross-attention follow the last encode. */
+int wb_set_audio_ctx(wb_ctx* ctx, int n_ctx);
 int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out);        /* `cur` after ln_post (1980-1984): [n_ctx][d] f32 */
 int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v); /* F16 bits [n_ctx][d], 2018-2030 */
 int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum);

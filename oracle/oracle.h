@@ -72,6 +72,7 @@ void orc_ctx_free(orc_ctx* ctx);
 int orc_get_hparams(const orc_ctx* ctx, int32_t out[11]);         /* 607-619 order */
 int orc_get_special_tokens(const orc_ctx* ctx, int32_t out[8]);   /* eot,sot,prev,solm,not,beg,translate,transcribe (557-575, 433-440) */
 int orc_set_option(orc_ctx* ctx, int opt, int value);
+int orc_set_audio_ctx(orc_ctx* ctx, int n_ctx);                   /* exp_n_audio_ctx, src/main.rs:362, 1803-1807 */
 
 /* whisper_pcm_to_mel (1681): whole clip, n_threads frame-strided workers (reference uses 4) */
 int orc_pcm_to_mel(orc_ctx* ctx, const float* pcm, size_t n_samples, int n_threads);

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         L.orc_get_hparams.argtypes = [vp, i32p]
         L.orc_get_special_tokens.argtypes = [vp, i32p]
         L.orc_set_option.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_set_audio_ctx.argtypes = [vp, C.c_int]
         L.orc_pcm_to_mel.argtypes = [vp, f32p, C.c_size_t, C.c_int]
         L.orc_mel_dims.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_mel_read.argtypes = [vp, f32p]
@@ -107,6 +108,11 @@ class Oracle:
         except Exception:
             pass
 
+    def set_audio_ctx(self, n_ctx: int) -> None:
+        """exp_n_audio_ctx (src/main.rs:362, 1803-1807); 0 = the model's n_audio_ctx."""
+        _check(lib().orc_set_audio_ctx(self._h, n_ctx))
+        self.audio_ctx = n_ctx or self.n_audio_ctx
+
     def set_option(self, opt: int, value: int) -> None:
         _check(lib().orc_set_option(self._h, opt, value))
 
@@ -130,12 +136,12 @@ class Oracle:
     # whisper_encode (src/main.rs:1799)
     def encode(self, mel_offset: int = 0, n_threads: Optional[int] = None) -> np.ndarray:
         _check(lib().orc_encode(self._h, n_threads or self.n_threads, mel_offset))
-        out = np.empty((self.n_audio_ctx, self.n_audio_state), dtype=np.float32)
+        out = np.empty((getattr(self, "audio_ctx", self.n_audio_ctx), self.n_audio_state), dtype=np.float32)
         _check(lib().orc_encoder_out_read(self._h, _f32p(out)))
         return out
 
     def cross_kv(self, layer: int) -> Tuple[np.ndarray, np.ndarray]:
-        k = np.empty((self.n_audio_ctx, self.n_text_state), dtype=np.float16)
+        k = np.empty((getattr(self, "audio_ctx", self.n_audio_ctx), self.n_text_state), dtype=np.float16)
         v = np.empty_like(k)
         _check(lib().orc_cross_kv_read(self._h, layer, k.ctypes.data_as(C.POINTER(C.c_uint16)),
                                        v.ctypes.data_as(C.POINTER(C.c_uint16))))

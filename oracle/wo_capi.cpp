@@ -47,6 +47,12 @@ int orc_set_option(orc_ctx* ctx, int opt, int value) {
   return ORC_OK;
 }
 
+int orc_set_audio_ctx(orc_ctx* ctx, int n_ctx) {   // exp_n_audio_ctx (src/main.rs:362); 0 = the model's
+  if (n_ctx < 0 || n_ctx > ctx->model.hp.n_audio_ctx) return ORC_ERR_UNEXPECTED;
+  ctx->exp_n_audio_ctx = n_ctx;
+  return ORC_OK;
+}
+
 int orc_pcm_to_mel(orc_ctx* ctx, const float* pcm, size_t n_samples, int n_threads) {
   return wo::pcm_to_mel(ctx, pcm, n_samples, n_threads);
 }
@@ -79,7 +85,7 @@ int orc_encoder_out_read(const orc_ctx* ctx, float* out) {
 
 int orc_cross_kv_read(const orc_ctx* ctx, int layer, uint16_t* k, uint16_t* v) {
   const auto& hp = ctx->model.hp;
-  const size_t n = (size_t)hp.n_audio_ctx * hp.n_text_state;
+  const size_t n = (size_t)(ctx->enc_n_ctx > 0 ? ctx->enc_n_ctx : hp.n_audio_ctx) * hp.n_text_state;
   if (layer < 0 || layer >= hp.n_text_layer || ctx->cross_k.size() < n * (layer + 1)) return ORC_ERR_UNEXPECTED;
   if (k) std::memcpy(k, ctx->cross_k.data() + n * layer, n * 2);
   if (v) std::memcpy(v, ctx->cross_v.data() + n * layer, n * 2);

@@ -133,6 +133,9 @@ struct orc_ctx {
   // mel (WhisperMel, src/main.rs:733-748)
   int mel_n_mel = 0, mel_n_len = 0;
   std::vector<float> mel;                 // [n_mel][n_len]
+  // exp_n_audio_ctx (src/main.rs:362, read at 1803-1807): > 0 shortens the audio context of whisper_encode
+  int exp_n_audio_ctx = 0;
+  int enc_n_ctx = 0;                      // the n_ctx the last encode ran with (rows of enc_out / cross K,V)
   // encoder results
   std::vector<float> enc_out;             // ln_post output [n_ctx][d]
   std::vector<uint16_t> cross_k, cross_v; // [L_text][n_ctx][d] F16 (memory_cross_k/v, 1350-1354)

@@ -18,7 +18,7 @@ int decode(orc_ctx* ctx, const int32_t* tokens, int N, int n_past, int n_threads
   const Model& m = ctx->model;
   const HParams& hp = m.hp;
   const int d = hp.n_text_state, H = hp.n_text_head, L = hp.n_text_layer;
-  const int n_ctx = hp.n_text_ctx, M = hp.n_audio_ctx, n_vocab = hp.n_vocab;
+  const int n_ctx = hp.n_text_ctx, M = ctx->enc_n_ctx > 0 ? ctx->enc_n_ctx : hp.n_audio_ctx, n_vocab = hp.n_vocab;
   if (N < 1 || n_past < 0 || n_past + N > n_ctx) return ORC_ERR_NOT_ENOUGH_SPACE;
   if (ctx->cross_k.size() != (size_t)L * M * d) return ORC_ERR_UNEXPECTED;   // encode first
   if (ctx->mem_k.size() != (size_t)L * n_ctx * d) {

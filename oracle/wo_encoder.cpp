@@ -88,7 +88,10 @@ static void add_bias_rows(float* y, int T, int N, const float* b) {
 int encode(orc_ctx* ctx, int n_threads, size_t mel_offset) {
   const Model& m = ctx->model;
   const HParams& hp = m.hp;
-  const int n_ctx = hp.n_audio_ctx;      // 1803-1807 (exp_n_audio_ctx is always 0)
+  // 1803-1807: exp_n_audio_ctx when positive (the reference never sets it: 500), else the model's audio context
+  const int n_ctx = ctx->exp_n_audio_ctx > 0 ? ctx->exp_n_audio_ctx : hp.n_audio_ctx;
+  if (n_ctx > hp.n_audio_ctx) return ORC_ERR_NOT_ENOUGH_SPACE;   // the positional embedding has n_audio_ctx rows
+  ctx->enc_n_ctx = n_ctx;
   const int d = hp.n_audio_state;
   const int H = hp.n_audio_head;
   const int L = hp.n_audio_layer;

@@ -119,3 +119,40 @@ def test_vocab_text_and_placeholder_names(pkg, model_path, tmp_path):
     with pytest.raises(api.WsError):
         ctx.token_text(51865)
     ctx.close()
+
+
+@pytest.mark.parametrize("arch,n_ctx", [("micro", 40), ("tiny", 700)])
+def test_exp_n_audio_ctx(pkg, pyoracle, model_path, arch, n_ctx):
+    """exp_n_audio_ctx (src/main.rs:362, 1803-1807): a shorter audio context -- window of 2 n_ctx frames, the first
+    n_ctx rows of the positional embedding -- through mel + encode + cross K/V + logits, against the oracle with the
+    same setting; back to the model's context afterwards."""
+    from whisper_rs_b200 import api
+    hp = pkg.ggml_file.ARCHS[arch]
+    n = 2 * hp.n_audio_ctx * 160
+    pcm = pkg.synth.make_segment(77, n, silent_tail_s=0.1)
+    ctx = api.WhisperContext.new(model_path(arch), max_segments=2, max_clips=1, max_clip_samples=n)
+    orc = pyoracle.Oracle(model_path(arch))
+    api.whisper_pcm_to_mel(ctx, pcm)
+    orc.pcm_to_mel(pcm)
+    with pytest.raises(api.WsError):
+        ctx.set_audio_ctx(hp.n_audio_ctx + 1)
+    ctx.set_audio_ctx(n_ctx)
+    orc.set_audio_ctx(n_ctx)
+    offs = [0, 2 * n_ctx]                                # two consecutive short windows in one batch
+    api.whisper_encode(ctx, 1, offs, clip_ids=[0, 0])
+    for s, off in enumerate(offs):
+        ref = orc.encode(off)
+        assert ref.shape == (n_ctx, hp.n_audio_state)
+        assert rel_l2(ctx.encoder_out(s), ref) < 1e-2, (s, rel_l2(ctx.encoder_out(s), ref))
+        k, v = ctx.cross_kv(s, hp.n_text_layer - 1)
+        rk, rv = orc.cross_kv(hp.n_text_layer - 1)
+        assert k.shape == (n_ctx, hp.n_text_state) and rel_l2(k, rk) < 1e-2 and rel_l2(v, rv) < 1e-2
+    # the decoder attends to the n_ctx rows of the last encode (sequence 1 <-> the oracle's last window)
+    toks = np.array([[3, 5, 8], [3, 5, 8]], dtype=np.int32)
+    api.whisper_decode(ctx, toks, 0)
+    assert rel_l2(ctx.logits(1), orc.decode(toks[1], 0)) < 1e-2
+    ctx.set_audio_ctx(0)
+    orc.set_audio_ctx(0)
+    api.whisper_encode(ctx, 1, 0)
+    assert rel_l2(ctx.encoder_out(0), orc.encode(0)) < 1e-2
+    ctx.close()

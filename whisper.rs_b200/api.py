@@ -78,6 +78,7 @@ class WhisperContext:
         (self.token_eot, self.token_sot, self.token_prev, self.token_solm, self.token_not,
          self.token_beg, self.token_translate, self.token_transcribe) = list(st)
         self.max_segments = max_segments
+        self.audio_ctx = self.n_audio_ctx        # exp_n_audio_ctx when set (set_audio_ctx), else the model's
 
     # ---- lifetime
     @classmethod
@@ -94,6 +95,11 @@ class WhisperContext:
             self.close()
         except Exception:
             pass
+
+    def set_audio_ctx(self, n_ctx: int) -> None:
+        """exp_n_audio_ctx (src/main.rs:362, 1803-1807): encode with n_ctx <= n_audio_ctx positions; 0 = the model's."""
+        _check(cabi.lib().wb_set_audio_ctx(self._h, n_ctx), self._h)
+        self.audio_ctx = n_ctx or self.n_audio_ctx
 
     def sync(self) -> None:
         _check(cabi.lib().wb_sync(self._h), self._h)
@@ -113,12 +119,12 @@ class WhisperContext:
         _check(cabi.lib().wb_mel_write(self._h, _f32p(mel), mel.shape[1], mel.shape[2], mel.shape[0]), self._h)
 
     def encoder_out(self, seg: int = 0) -> np.ndarray:
-        out = np.empty((self.n_audio_ctx, self.n_audio_state), dtype=np.float32)
+        out = np.empty((self.audio_ctx, self.n_audio_state), dtype=np.float32)
         _check(cabi.lib().wb_encoder_out_read(self._h, seg, _f32p(out)), self._h)
         return out
 
     def cross_kv(self, seg: int, layer: int) -> Tuple[np.ndarray, np.ndarray]:
-        k = np.empty((self.n_audio_ctx, self.n_text_state), dtype=np.float16)
+        k = np.empty((self.audio_ctx, self.n_text_state), dtype=np.float16)
         v = np.empty_like(k)
         u16 = C.POINTER(C.c_uint16)
         _check(cabi.lib().wb_cross_kv_read(self._h, seg, layer, k.ctypes.data_as(u16), v.ctypes.data_as(u16)), self._h)

@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.wb_mel_read.argtypes = [vp, C.c_int, f32p, C.c_size_t]
     L.wb_mel_write.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int]
     L.wb_encode.argtypes = [vp, i32p, C.POINTER(C.c_size_t), C.c_int]
+    L.wb_set_audio_ctx.argtypes = [vp, C.c_int]
     L.wb_encoder_out_read.argtypes = [vp, C.c_int, f32p]
     L.wb_cross_kv_read.argtypes = [vp, C.c_int, C.c_int, u16p, u16p]
     L.wb_checksum.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]

@@ -996,7 +996,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: no mel in the context (call wb_pcm_to_mel first)");
   if (!ctx->mel_normalized)
     return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: the mel is not normalised (call wb_mel_normalize after wb_pcm_to_logmel)");
-  const int T = hp.n_audio_ctx, Tm = 2 * T, d = hp.n_audio_state, H = hp.n_audio_head, L = hp.n_audio_layer;
+  // 1803-1807: exp_n_audio_ctx when positive (wb_set_audio_ctx), else the model's audio context
+  const int T = ctx->exp_n_audio_ctx > 0 ? ctx->exp_n_audio_ctx : hp.n_audio_ctx;
+  const int Tm = 2 * T, d = hp.n_audio_state, H = hp.n_audio_head, L = hp.n_audio_layer;
   const int Lt = hp.n_text_layer, n_mels = hp.n_mels;
   const int M = n_seg * T;
   const bool chk = ctx->cfg.checkpoints != 0;
@@ -1207,14 +1209,24 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   cudaEventRecord(ctx->ev[1][1], st);
   ctx->ev_used[1] = true;
   ctx->enc_n_seg = n_seg;
+  ctx->enc_T = T;
   ctx->tm.n_encode_calls += 1;
+  return WB_OK;
+}
+
+// exp_n_audio_ctx (src/main.rs:362, read at 1803-1807; the reference initialises it to 0 and never sets it)
+int wb_set_audio_ctx(wb_ctx* ctx, int n_ctx) {
+  if (!ctx) return WB_ERR_UNEXPECTED;
+  if (n_ctx < 0 || n_ctx > ctx->hp.n_audio_ctx)   // the positional embedding has n_audio_ctx rows (960)
+    return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: audio context out of range");
+  ctx->exp_n_audio_ctx = n_ctx;
   return WB_OK;
 }
 
 int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out) {
   if (!ctx || !out || seg < 0 || seg >= ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const size_t n = (size_t)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  const size_t n = (size_t)ctx->enc_T * ctx->hp.n_audio_state;
   WB_CK(cudaMemcpyAsync(out, ctx->enc_out + (size_t)seg * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
   return WB_OK;
@@ -1223,7 +1235,7 @@ int wb_encoder_out_read(wb_ctx* ctx, int seg, float* out) {
 int wb_cross_kv_read(wb_ctx* ctx, int seg, int layer, uint16_t* k, uint16_t* v) {
   if (!ctx || seg < 0 || seg >= ctx->enc_n_seg || layer < 0 || layer >= ctx->hp.n_text_layer) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const size_t n = (size_t)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  const size_t n = (size_t)ctx->enc_T * ctx->hp.n_audio_state;
   // the reference's dense [n_ctx][d] slice of memory_cross_k/v (2018-2030)
   const __half* kb = ctx->cross + (size_t)(2 * layer) * ctx->cross_slab + (size_t)seg * n;
   const __half* vb = ctx->cross + (size_t)(2 * layer + 1) * ctx->cross_slab + (size_t)seg * n;
@@ -1248,7 +1260,7 @@ int wb_checksum(wb_ctx* ctx, int stage, int layer, int seg, double* abs_sum) {
 int wb_encoder_digest(wb_ctx* ctx, double* out, int cap) {
   if (!ctx || !out || ctx->enc_n_seg < 1 || cap < ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const long long n = (long long)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  const long long n = (long long)ctx->enc_T * ctx->hp.n_audio_state;
   double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
   {
     LaunchTimer t(ctx, "digest");
@@ -1264,7 +1276,7 @@ int wb_encoder_digest(wb_ctx* ctx, double* out, int cap) {
 int wb_encoder_digest_async(wb_ctx* ctx, double* out, int cap) {
   if (!ctx || !out || ctx->enc_n_seg < 1 || cap < ctx->enc_n_seg) return WB_ERR_UNEXPECTED;
   cudaSetDevice(ctx->device);
-  const long long n = (long long)ctx->hp.n_audio_ctx * ctx->hp.n_audio_state;
+  const long long n = (long long)ctx->enc_T * ctx->hp.n_audio_state;
   double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
   {
     LaunchTimer t(ctx, "digest");

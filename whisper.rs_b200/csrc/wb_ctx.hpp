@@ -121,6 +121,8 @@ struct wb_ctx {
   size_t cross_slab = 0;              // elements per slab = max_segments * T * d
   int Tp = 0;
   int enc_n_seg = 0;                  // segments of the last wb_encode
+  int exp_n_audio_ctx = 0;            // exp_n_audio_ctx (src/main.rs:362): > 0 shortens the encoder's audio context
+  int enc_T = 0;                      // audio context the last wb_encode ran with (rows per segment of its outputs)
   double* d_chk = nullptr;            // [slot][max_segments]
   int n_chk_slots = 0;
   std::vector<char> chk_valid;

@@ -194,7 +194,8 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
   const ModelHParams& hp = ctx->hp;
   const bool skip_cross = dec_skip("cross"), skip_self = dec_skip("self"), skip_lin = dec_skip("linear"),
              skip_logits = dec_skip("logits");
-  const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, T = hp.n_audio_ctx;
+  const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer;
+  const int T = ctx->enc_T > 0 ? ctx->enc_T : hp.n_audio_ctx;   // rows of the cross K/V the last wb_encode wrote
   const int n_ctx = hp.n_text_ctx;
   const int R = n_seq * n_tok;
   const long long ld_kv = d;   // cross K / V of one layer: dense [seg][T][d]

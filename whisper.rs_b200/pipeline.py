@@ -62,7 +62,7 @@ def transcribe_clip(ctx: api.WhisperContext, pcm: np.ndarray, *, rank: int = 0, 
     ranks (None for world == 1).  Returns (window ids, tokens [n_local][max_new], lengths, margins)."""
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
     total = int(n_samples_total if pcm_is_local_span else pcm.size)
-    part = ClipPart(total, rank, world, 2 * ctx.n_audio_ctx)
+    part = ClipPart(total, rank, world, 2 * ctx.audio_ctx)
     if world > 1 and reduce_max is None:
         raise ValueError("world > 1 needs reduce_max (the whole-clip maximum couples the parts)")
     local_max = -1e20                                   # mmax's initial value (1655)
@@ -115,7 +115,7 @@ def assemble_segments(ctx: api.WhisperContext, windows: Sequence[int], toks: np.
     [3000 w, 3000 (w + 1)) centiseconds (clipped to the clip's length when `n_samples` is given); a time-stamp token
     (id >= token_beg, 568) carries (id - token_beg) * 2 centiseconds relative to its window and ends the run of text
     tokens before it; text = the window's text tokens (ids below eot) through id_to_token (544)."""
-    fpw = 2 * ctx.n_audio_ctx
+    fpw = 2 * ctx.audio_ctx
     out: List[WhisperSegment] = []
     for i, w in enumerate(windows):
         n = int(lens[i])

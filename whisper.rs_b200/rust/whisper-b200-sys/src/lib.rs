@@ -70,6 +70,7 @@ extern "C" {
     pub fn wb_mel_read(ctx: *mut wb_ctx, clip: c_int, out: *mut f32, cap_floats: usize) -> c_int;
     pub fn wb_mel_write(ctx: *mut wb_ctx, mel: *const f32, n_mel: c_int, n_len: c_int, n_clips: c_int) -> c_int;
     pub fn wb_encode(ctx: *mut wb_ctx, clip_ids: *const i32, mel_offsets: *const usize, n_segments: c_int) -> c_int;
+    pub fn wb_set_audio_ctx(ctx: *mut wb_ctx, n_ctx: c_int) -> c_int;
     pub fn wb_encoder_out_read(ctx: *mut wb_ctx, seg: c_int, out: *mut f32) -> c_int;
     pub fn wb_cross_kv_read(ctx: *mut wb_ctx, seg: c_int, layer: c_int, k: *mut u16, v: *mut u16) -> c_int;
     pub fn wb_checksum(ctx: *mut wb_ctx, stage: c_int, layer: c_int, seg: c_int, abs_sum: *mut f64) -> c_int;
