@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(128)
 embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
              int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, float2* __restrict__ stats,
              __half* __restrict__ x16, int n_clear) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
+  pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ float red[2][4];
   const int row = blockIdx.x;   // s * n_tok + i
   const int i = row % n_tok;
@@ -113,8 +113,8 @@ constexpr int SELF_U = 8;          // key / value rows per lane requested before
 __global__ void __launch_bounds__(SELF_THREADS)
 decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restrict__ kc, __half* __restrict__ vc,
                         int n_tok, const int* __restrict__ n_past_p, int n_text_ctx, __half* __restrict__ out) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
+  pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ float sc[SELF_MAX_CTX];
   __shared__ float red[SELF_THREADS / 32];
   __shared__ float opart[SELF_THREADS / 32][4][DH];
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ next_tok, float* __restrict__ margin_out,
               int* __restrict__ out_tokens, float* __restrict__ out_margin, int* __restrict__ out_len,
               int* __restrict__ done, int max_new, const int* __restrict__ step_p, int eot) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
+  pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ Top2 sh[32];
   const int s = blockIdx.x;
   const float* lg = logits + (size_t)s * n_vocab;
@@ -709,8 +709,8 @@ argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restri
                        float* __restrict__ margin_out, int* __restrict__ out_tokens, float* __restrict__ out_margin,
                        int* __restrict__ out_len, int* __restrict__ done, int max_new, const int* __restrict__ step_p,
                        int eot) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
+  pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ Top2 sh[8];
   const int s = blockIdx.x;
   const float* p = part + (size_t)s * n_part * 3;
@@ -747,8 +747,8 @@ argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restri
 }
 
 __global__ void advance_kernel(int* n_past, int add, int* step) {
-  pdl_wait();   // launched with programmatic stream serialisation: the launch overlapped the previous kernel
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
+  pdl_wait();                // everything this kernel reads is the previous kernels' output
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *n_past += add;
     if (step) *step += 1;

@@ -16,8 +16,8 @@ namespace {
 __global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
                                   const long long* __restrict__ offsets, int Tm, __half* __restrict__ out) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();   // the next kernel may become resident now; it blocks at its own wait
   pdl_wait();
-  pdl_launch_dependents();
   const int seg = blockIdx.z;
   const int clip = clip_ids ? clip_ids[seg] : 0;
   const long long off = offsets ? offsets[seg] : 0;
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long in_row_stride, const float* __restrict__ w,
                  const float* __restrict__ b, int rows, int d, __half* __restrict__ out_f16,
                  float* __restrict__ out_f32) {
+  pdl_launch_dependents();   // the next kernel may become resident now; it blocks at its own wait
   pdl_wait();
-  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int row0 = warp * RPW;
