@@ -363,7 +363,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
               }
             }
             if (GELU) {
-              x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
+              gelu_f16in_x2(x0, x1);
+              gelu_f16in_x2(x2, x3);
             }
             r0[4 * g] = __float_as_uint(x0); r0[4 * g + 1] = __float_as_uint(x1);
             r0[4 * g + 2] = __float_as_uint(x2); r0[4 * g + 3] = __float_as_uint(x3);
@@ -388,7 +389,8 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
                 }
               }
               if (GELU) {
-                x0 = gelu_f16in(x0); x1 = gelu_f16in(x1); x2 = gelu_f16in(x2); x3 = gelu_f16in(x3);
+                gelu_f16in_x2(x0, x1);
+              gelu_f16in_x2(x2, x3);
               }
               r1[4 * g] = __float_as_uint(x0); r1[4 * g + 1] = __float_as_uint(x1);
               r1[4 * g + 2] = __float_as_uint(x2); r1[4 * g + 3] = __float_as_uint(x3);

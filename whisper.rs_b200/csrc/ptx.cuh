@@ -476,5 +476,26 @@ __device__ __forceinline__ float gelu_f16in(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// The same for two values: one F16 rounding for the pair and the polynomial in packed f32x2 (about 5 issue slots
+// per element instead of 9 -- at K = 512 the GEMM epilogue, not the tensor pipe, sets the tile rate).
+__device__ __forceinline__ void gelu_f16in_x2(float& x0, float& x1) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 xf = __half22float2(h);
+  const uint64_t x = f2_pack(xf.x, xf.y);
+  const uint64_t x2 = f2_mul(x, x);
+  const uint64_t inner = f2_fma(x2, f2_pack(0.044715f * 0.79788456080286535588f, 0.044715f * 0.79788456080286535588f),
+                                f2_pack(0.79788456080286535588f, 0.79788456080286535588f));
+  float u0, u1, t0, t1;
+  f2_unpack(f2_mul(x, inner), u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t hx = f2_mul(x, f2_pack(0.5f, 0.5f));
+  f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), x0, x1);
+}
 
 }  // namespace wb
