@@ -82,7 +82,10 @@ int wb_get_special_tokens(const wb_ctx* ctx, int32_t out[8]);     /* WhisperVoca
 /* whisper_pcm_to_mel (1681-1707) -> log_mel_spectrogram (1554-1652) + clamp_and_normalize
  * (1654-1671), for n_clips clips of n_samples each.  The result stays on the device, like
  * ctx.mel (349).  `pcm` is a HOST pointer ([n_clips][n_samples] f32); the _device variant takes a
- * device pointer (inputs already resident in HBM). */
+ * device pointer (inputs already resident in HBM).  The calls do not wait for the GPU: with PINNED host
+ * memory the upload is asynchronous, so the buffer must stay unchanged until a later blocking call on the
+ * handle (wb_sync, wb_wait, any read-back) has returned -- the reference holds its samples in an
+ * Arc<Vec<f32>> for the same reason (1584, 1681); pageable memory is staged before the call returns. */
 int wb_pcm_to_mel(wb_ctx* ctx, const float* pcm, size_t n_samples, int n_clips);
 int wb_pcm_to_mel_device(wb_ctx* ctx, const float* pcm_dev, size_t n_samples, int n_clips);
 /* same with i16 PCM, the reference's real input: convert_integer_to_float_audio (1673-1679) */
