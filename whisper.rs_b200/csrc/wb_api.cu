@@ -476,20 +476,6 @@ int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
     if (lo >= hi) lo = hi = 0;
     range[j] = make_int2(lo, hi);
   }
-  float *d_hann, *d_filt;
-  float2 *d_w200, *d_w400;
-  int2* d_range;
-  int rc;
-  if ((rc = dev_alloc(ctx, &d_hann, 400, false))) return rc;
-  if ((rc = dev_alloc(ctx, &d_w200, 200, false))) return rc;
-  if ((rc = dev_alloc(ctx, &d_w400, 201, false))) return rc;
-  if ((rc = dev_alloc(ctx, &d_filt, filt.size(), false))) return rc;
-  if ((rc = dev_alloc(ctx, &d_range, (size_t)n_mel, false))) return rc;
-  WB_CK(cudaMemcpy(d_hann, hann.data(), 1600, cudaMemcpyHostToDevice));
-  WB_CK(cudaMemcpy(d_w200, w200.data(), 1600, cudaMemcpyHostToDevice));
-  WB_CK(cudaMemcpy(d_w400, w400.data(), 1608, cudaMemcpyHostToDevice));
-  WB_CK(cudaMemcpy(d_filt, filt.data(), filt.size() * 4, cudaMemcpyHostToDevice));
-  WB_CK(cudaMemcpy(d_range, range.data(), (size_t)n_mel * 8, cudaMemcpyHostToDevice));
   // compact taps: [lo, hi) of each mel back to back (zeros inside the span are kept: the sum order stays bin order)
   std::vector<float> nz;
   std::vector<int> start(n_mel);
@@ -499,13 +485,22 @@ int build_mel_tables(wb_ctx* ctx, const ModelFileView& mv) {
   }
   if (nz.size() > 1024 || n_mel > 128)
     return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: mel filterbank too dense for the front-end kernel");
-  float* d_nz;
-  int* d_start;
-  if ((rc = dev_alloc(ctx, &d_nz, nz.size() ? nz.size() : 1, false))) return rc;
-  if ((rc = dev_alloc(ctx, &d_start, (size_t)n_mel, false))) return rc;
-  WB_CK(cudaMemcpy(d_nz, nz.data(), nz.size() * 4, cudaMemcpyHostToDevice));
-  WB_CK(cudaMemcpy(d_start, start.data(), (size_t)n_mel * 4, cudaMemcpyHostToDevice));
-  ctx->mel_tab = MelTables{d_hann, d_w200, d_w400, d_filt, d_range, n_mel, d_nz, d_start, (int)nz.size()};
+  std::vector<MelTableBlob> blob(1);
+  MelTableBlob& b = blob[0];
+  memset(&b, 0, sizeof(b));
+  memcpy(b.w200, w200.data(), sizeof(float2) * 200);
+  memcpy(b.w400, w400.data(), sizeof(float2) * 201);
+  memcpy(b.hann, hann.data(), sizeof(float) * 400);
+  memcpy(b.fw, nz.data(), sizeof(float) * nz.size());
+  for (int j = 0; j < n_mel; ++j) {
+    b.frange[j] = make_int2(range[j].x, start[j]);
+    b.fcount[j] = range[j].y - range[j].x;
+  }
+  MelTableBlob* d_blob = nullptr;
+  int rc;
+  if ((rc = dev_alloc(ctx, &d_blob, 1, false))) return rc;
+  WB_CK(cudaMemcpy(d_blob, &b, sizeof(b), cudaMemcpyHostToDevice));
+  ctx->mel_tab = MelTables{d_blob, n_mel};
   return WB_OK;
 }
 

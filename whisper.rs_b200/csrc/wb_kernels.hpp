@@ -121,16 +121,20 @@ cudaError_t launch_vt_init(__half* vt, int n_heads_total, int Tp, cudaStream_t s
 bool attention_setup_attributes(const char** err);
 
 // ---- log-mel (src/main.rs:1554-1671) -----------------------------------------------------------
-struct MelTables {            // device pointers, built once per context
-  const float* hann;          // [400]
-  const float2* tw200;        // W_200^j, j < 200
-  const float2* tw400;        // W_400^k, k <= 200
-  const float* filt;          // [n_mel][201]
-  const int2* filt_range;     // per mel: [lo, hi) of nonzero taps
+// every table the mel kernel needs, laid out exactly as it sits in shared memory: each CTA copies the blob
+// verbatim with 16-byte loads that are all in flight together
+struct MelTableBlob {
+  float2 w200[200];           // W_200^j, j < 200
+  float2 w400[202];           // W_400^k, k <= 200 (+ 1 of padding: every member starts on 16 bytes)
+  float hann[400];            // periodic Hann window (1567-1569)
+  float fw[1024];             // non-zero filterbank taps, mel after mel (bin order inside a mel)
+  int2 frange[128];           // per mel: first bin, first tap index in fw
+  int fcount[128];            // per mel: number of taps
+};
+static_assert(sizeof(MelTableBlob) % 16 == 0, "copied as float4");
+struct MelTables {            // built once per context
+  const MelTableBlob* blob;   // device
   int n_mel;
-  const float* filt_nz;       // the taps of [lo, hi) of every mel, concatenated
-  const int* filt_start;      // per mel: offset of its first tap in filt_nz
-  int n_nz;
 };
 // frames -> log10 mel power, [clip][n_mel][n_len]; also per-clip running max (ordered-int encoding)
 cudaError_t launch_mel_frames(const MelTables& t, const void* pcm, int pcm_is_i16, size_t n_samples,
