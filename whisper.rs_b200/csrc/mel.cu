@@ -25,7 +25,8 @@ namespace {
 constexpr int F = 16;                        // frames per CTA
 constexpr int NFFT = 400, HOP = 160, NBIN = 201;
 constexpr int SPAN = HOP * (F - 1) + NFFT;   // 2800 samples
-constexpr int MEL_THREADS = 128;             // F frames x 8 (pass A: one 25-point DFT per thread)
+constexpr int MEL_THREADS = 256;             // pass A uses F x 8 = 128 of them (one 25-point DFT per thread); passes B (208
+                                             // items) and C (F x n_mel) and the staging copies use all
 constexpr int MEL_MAX_NZ = 1024, MEL_MAX_MEL = 128;
 // the sample span is stored skewed, sample j at j + 16 (j / 160): frame f starts 160 f samples in, a multiple
 // of the 32 banks, so the four frames a warp reads together would otherwise hit the same banks
@@ -174,7 +175,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
   __syncthreads();
 
   // ---- pass A: window + 25-point DFT over n2 in registers + twiddle W200^(n1 k2)
-  {
+  if (tid < F * 8) {
     const int f = tid >> 3, n1 = tid & 7;
     float2 z[25];
 #pragma unroll
@@ -255,7 +256,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
     float sum = 0.0f;
     for (int k = 0; k < nt; ++k) sum = fmaf(pw[k], fw[k], sum);
     sum = fmaxf(sum, 1e-10f);
-    const float v = log10f(sum);
+    const float v = __log10f(sum);   // lg2.approx * log10(2): abs. error ~1e-7, far inside the 1e-4 the front end is held to
     out[(size_t)j * n_len + i] = v;
     tmax = fmaxf(tmax, v);
   }
