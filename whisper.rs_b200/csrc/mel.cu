@@ -118,7 +118,7 @@ __device__ __forceinline__ float bin_power(float2 zk, float2 zo, float2 w, int k
 // One shared-memory round trip for the FFT instead of four, ~2.5x fewer instructions per frame than the
 // pass-per-radix version it replaces (which was issue-bound: 5 passes x ~4 k cycles per 16 frames).
 template <bool I16>
-__global__ void __launch_bounds__(MEL_THREADS)
+__global__ void __launch_bounds__(MEL_THREADS, 4)   // 64 registers: four CTAs (32 warps) per SM
 mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_samples, int n_len,
                   float* __restrict__ mel_out, int* __restrict__ clip_max_enc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
