@@ -11,30 +11,31 @@ namespace {
 // its source and with the transpose to token-major rows the conv-as-GEMM reads through TMA:
 //   in  mel [clip][n_mel][n_len] f32 (time contiguous)
 //   out [seg][Tm + 2][n_mel] f16, rows 0 and Tm+1 stay zero (the conv's zero padding)
-// 32 x 32 tiles through shared memory so both the read (along time) and the write (along mel)
-// are coalesced.
-__global__ void mel_window_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
-                                  const long long* __restrict__ offsets, int Tm, __half* __restrict__ out) {
-  __shared__ float tile[32][33];
+// (all mel rows) x 32-frame tiles through shared memory so both the read (along time) and the write
+// (along mel) are coalesced.
+constexpr int MW_MAX_MEL = 128;
+__global__ void __launch_bounds__(256)
+mel_window_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
+                  const long long* __restrict__ offsets, int Tm, __half* __restrict__ out) {
+  // a tile = every mel row x 32 frames: the 32 output rows (n_mel halves each) are one contiguous run of memory
+  __shared__ float tile[MW_MAX_MEL][33];
   pdl_launch_dependents();   // the next kernel may become resident now; it blocks at its own wait
   pdl_wait();
   const int seg = blockIdx.z;
   const int clip = clip_ids ? clip_ids[seg] : 0;
   const long long off = offsets ? offsets[seg] : 0;
   const float* src = mel + (size_t)clip * n_mel * n_len;
-  const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int j = j0 + r, t = t0 + threadIdx.x;
-    const long long i = off + t;
-    float v = 0.0f;
-    if (j < n_mel && t < Tm && i < n_len) v = src[(size_t)j * n_len + i];   // zero past the clip end (1820-1828)
-    tile[r][threadIdx.x] = v;
-  }
+  const int t0 = blockIdx.x * 32;
+  const int t_in = t0 + threadIdx.x;
+  const long long i_in = off + t_in;
+  const bool in_ok = t_in < Tm && i_in < n_len;   // zero past the clip end (1820-1828)
+  for (int j = threadIdx.y; j < n_mel; j += blockDim.y) tile[j][threadIdx.x] = in_ok ? src[(size_t)j * n_len + i_in] : 0.0f;
   __syncthreads();
   __half* dst = out + (size_t)seg * (Tm + 2) * n_mel;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int t = t0 + r, j = j0 + threadIdx.x;
-    if (t < Tm && j < n_mel) dst[(size_t)(t + 1) * n_mel + j] = __float2half_rn(tile[threadIdx.x][r]);
+    const int t = t0 + r;
+    if (t >= Tm) break;
+    for (int j = threadIdx.x; j < n_mel; j += 32) dst[(size_t)(t + 1) * n_mel + j] = __float2half_rn(tile[j][r]);
   }
 }
 
@@ -153,7 +154,8 @@ __global__ void abs_sum_f16_kernel(const __half* __restrict__ x, int rows, int c
 
 cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int* clip_ids, const long long* offsets,
                               int n_seg, int Tm, __half* out, cudaStream_t st) {
-  dim3 grid((Tm + 31) / 32, (n_mel + 31) / 32, n_seg);
+  if (n_mel > MW_MAX_MEL) return cudaErrorInvalidValue;
+  dim3 grid((Tm + 31) / 32, 1, n_seg);
   return launch_pdl(mel_window_kernel, grid, dim3(32, 8), 0, st, mel, n_mel, n_len, clip_ids, offsets, Tm, out);
 }
 
