@@ -1017,9 +1017,15 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   WB_CK(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(long long) * n_seg, cudaMemcpyHostToDevice, st));
   WB_CK(cudaEventRecord(ctx->ev_seg_slot[slot], st));
 
-  // ---- tensor maps of the activation operands for this batch size
-  CUtensorMap m_conv1, m_conv2, m_ln, m_att, m_hid, m_enc;
-  AttnProblem ap;
+  // ---- tensor maps of the activation operands: they depend only on the batch size and the audio context, so
+  // they are encoded once per (n_seg, T) and kept in the handle (17 cuTensorMapEncodeTiled calls per encode
+  // otherwise: a third of the call's host time)
+  wb::EncodeMaps& em = ctx->enc_maps;
+  CUtensorMap &m_conv1 = em.m_conv1, &m_conv2 = em.m_conv2, &m_ln = em.m_ln, &m_att = em.m_att, &m_hid = em.m_hid, &m_enc = em.m_enc;
+  CUtensorMap &o_conv1 = em.o_conv1, &o_x3 = em.o_x3, &o_pe = em.o_pe, &o_x = em.o_x, &o_qk = em.o_qk, &o_hid = em.o_hid, &o_cross = em.o_cross;
+  AttnProblem& ap = em.ap;
+  if (em.n_seg != n_seg || em.T != T) {
+  em.n_seg = 0;
   bool ok = tmap_3d_rows(&m_conv1, ctx->conv_in, 3 * n_mels, Tm, n_seg, n_mels, (uint64_t)(Tm + 2) * n_mels, &terr) &&
             tmap_3d_rows(&m_conv2, ctx->h1, 3 * d, T, n_seg, 2 * d, (uint64_t)(Tm + 2) * d, &terr) &&
             tmap_3d_rows(&m_ln, ctx->ln_out, d, M, 1, d, (uint64_t)M * d, &terr) &&
@@ -1049,7 +1055,6 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     ap.has_map64 = ok;
   }
   // epilogue output / residual boxes of the pair GEMM
-  CUtensorMap o_conv1, o_x3, o_pe, o_x, o_qk, o_hid, o_cross;
   ok = ok && tmap_out(&o_conv1, ctx->h1 + d, false, d, Tm, n_seg, d, (uint64_t)(Tm + 2) * d, &terr) &&
        tmap_out(&o_x3, ctx->x, true, d, T, n_seg, d, (uint64_t)T * d, &terr) &&
        tmap_out(&o_pe, ctx->e_pe, true, d, T, 1, d, 0, &terr) &&
@@ -1063,6 +1068,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   ap.H = H;
   ap.out = ctx->attn_out;
   ap.scale = 1.0f / sqrtf(64.0f);
+  em.n_seg = n_seg;
+  em.T = T;
+  }
 
   auto probe_f32 = [&](int slot, const float* p, long long per_seg, long long seg_stride) -> int {
     WB_CK(launch_abs_sum_f32(p, per_seg, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, st));

@@ -41,6 +41,13 @@ struct ActMaps {          // one activation buffer as the skinny GEMM operand, p
   CUtensorMap m[4];       // box {64, 32|64|128|256}
 };
 
+struct EncodeMaps {       // wb_encode's tensor maps for one (n_seg, audio context); rebuilt when either changes
+  int n_seg = 0, T = 0;
+  CUtensorMap m_conv1, m_conv2, m_ln, m_att, m_hid, m_enc;               // A operands
+  CUtensorMap o_conv1, o_x3, o_pe, o_x, o_qk, o_hid, o_cross;            // epilogue output / residual boxes
+  AttnProblem ap;
+};
+
 struct PendingEvent {   // one bracketed launch whose events have not been read yet
   const char* fam;
   cudaEvent_t a, b;
@@ -120,6 +127,7 @@ struct wb_ctx {
                                       // 2*il, V is slab 2*il+1 (each a dense [seg][T][d] matrix, as in src/main.rs:2018-2030)
   size_t cross_slab = 0;              // elements per slab = max_segments * T * d
   int Tp = 0;
+  wb::EncodeMaps enc_maps;
   int enc_n_seg = 0;                  // segments of the last wb_encode
   int exp_n_audio_ctx = 0;            // exp_n_audio_ctx (src/main.rs:362): > 0 shortens the encoder's audio context
   int enc_T = 0;                      // audio context the last wb_encode ran with (rows per segment of its outputs)
