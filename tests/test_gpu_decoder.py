@@ -105,6 +105,29 @@ def test_micro_greedy(pkg, pyoracle, model_path, golden):
     ctx.close()
 
 
+def test_micro_greedy_more_than_32_sequences(pkg, pyoracle, model_path, golden):
+    """40 sequences: a single-token step has more than 32 rows, so every linear takes the tcgen05 swap-AB GEMM
+    behind a plain LayerNorm and the arg-max reads the full logits (no per-CTA top-2 partials)."""
+    from whisper_rs_b200 import api
+    n = int(golden["n_samples"])
+    S = 40
+    ctx = api.WhisperContext.new(model_path("micro"), max_segments=S, max_clips=S, max_clip_samples=n)
+    clips = np.stack([pkg.synth.make_segment(200 + s, n, 0.2) for s in range(S)])
+    api.whisper_pcm_to_mel(ctx, clips)
+    api.whisper_encode(ctx, 1, [0] * S, clip_ids=list(range(S)))
+    eot = ctx.n_vocab - 1
+    toks, marg, lens = api.whisper_decode_greedy(ctx, [7], 6, n_seqs=S, eot=eot)
+    agree = 0
+    for s in (0, 17, 33, 39):
+        o = pyoracle.Oracle(model_path("micro"))
+        o.pcm_to_mel(clips[s])
+        o.encode(0)
+        rt, rm = o.decode_greedy([7], 6, eot=eot)
+        agree += _check_greedy(toks[s], lens[s], rt, rm)
+    assert agree >= 8
+    ctx.close()
+
+
 def test_greedy_stops_at_eot(pkg, pyoracle, model_path, golden):
     from whisper_rs_b200 import api
     ctx, orcs = _setup(pkg, pyoracle, model_path, "micro", 1, int(golden["n_samples"]))
