@@ -47,9 +47,12 @@ typedef struct wb_config {
   int32_t max_segments;    /* encoder/decoder batch capacity (30 s windows per wb_encode call) */
   int32_t max_clips;       /* clips per wb_pcm_to_mel call */
   int64_t max_clip_samples;/* longest clip, in samples */
-  int32_t norm_scope;      /* WB_NORM_CLIP = whole-clip max as clamp_and_normalize (1654-1671); the only scope
-                              implemented (wb_ctx_create rejects others).  A clip split across GPUs keeps the
-                              whole-clip maximum through wb_pcm_to_logmel / wb_mel_normalize */
+  int32_t norm_scope;      /* WB_NORM_CLIP = whole-clip max as clamp_and_normalize (1654-1671), the reference's
+                              behaviour (a clip split across GPUs keeps the whole-clip maximum through
+                              wb_pcm_to_logmel / wb_mel_normalize).  WB_NORM_SEGMENT = every encoder window is
+                              clamped against its OWN maximum (what the reference computes for a clip of exactly
+                              that window): windows become fully independent; the stored mel (wb_mel_read) then
+                              holds the un-normalised log10 values */
   int32_t checkpoints;     /* 1: keep sum|x| probes per stage (the author's debug probes, 1836-1849) */
   void*   stream;          /* cudaStream_t to run on; NULL = the library creates its own */
   int32_t decode_capacity; /* 1: allocate self-attention KV for max_segments sequences */
@@ -141,7 +144,9 @@ int wb_wait(wb_ctx* ctx, int ticket);
 int wb_decode(wb_ctx* ctx, const int32_t* tokens, int n_tokens, int n_past, int n_seqs);
 int wb_logits_read(wb_ctx* ctx, int seq, float* out);             /* [n_vocab] f32 */
 /* greedy loop on the device: arg-max over all logits, stop per sequence at `eot` or max_new.
- * out_tokens [n_seqs][max_new], out_margin (top1 - top2 logit, may be NULL), out_len [n_seqs]. */
+ * out_tokens [n_seqs][max_new], out_margin (top1 - top2 logit, may be NULL), out_len [n_seqs].
+ * At most n_text_ctx tokens are generated per sequence whatever max_new says; the row stride of the
+ * output arrays stays the caller's max_new (columns past the generated ones are left untouched). */
 int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_new, int eot,
                      int n_seqs, int32_t* out_tokens, float* out_margin, int32_t* out_len);
 

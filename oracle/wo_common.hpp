@@ -70,6 +70,14 @@ struct Tensor {
   const uint16_t* h() const { return reinterpret_cast<const uint16_t*>(data.data()); }
   // weight rows as f32 (F16 -> F32 is exact)
   void to_f32(std::vector<float>& out) const;
+  // the same, converted once and kept (a decode step walks every decoder weight: converting them at every
+  // call made the oracle's per-token time ~10x its arithmetic).  Called from the driving thread only.
+  const float* f32_rows() const {
+    if (!f16) return f32();
+    if (f32_cache.empty()) to_f32(f32_cache);
+    return f32_cache.data();
+  }
+  mutable std::vector<float> f32_cache;
 };
 
 struct HParams {  // src/main.rs:607-619
@@ -139,6 +147,7 @@ struct orc_ctx {
   // encoder results
   std::vector<float> enc_out;             // ln_post output [n_ctx][d]
   std::vector<uint16_t> cross_k, cross_v; // [L_text][n_ctx][d] F16 (memory_cross_k/v, 1350-1354)
+  std::vector<float> cross_kf, cross_vf;  // the same values widened to f32 once per encode (decoder's operand form)
   std::vector<uint16_t> mem_k, mem_v;     // [L_text][n_text_ctx][d] F16 (memory_k/v, 1346-1347)
   std::map<int, double> chk;              // stage*1000+layer -> sum|x|
   std::vector<float> logits;              // [n_vocab] of the last decoded position

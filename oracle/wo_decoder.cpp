@@ -26,6 +26,10 @@ int decode(orc_ctx* ctx, const int32_t* tokens, int N, int n_past, int n_threads
     ctx->mem_v.assign((size_t)L * n_ctx * d, 0);
   }
   const float qk_scale = powf((float)d / (float)H, -0.25f);
+  // a single-token step does too little work per op to pay for spawning workers (parallel_for starts fresh
+  // threads at every call): the per-layer ops run on the calling thread, only the vocabulary projection is split
+  const int nt_all = n_threads;
+  if ((size_t)N * d * d < ((size_t)1 << 24)) n_threads = 1;
 
   // D1: x = d_te[:, tok] + d_pe[:, n_past + i]
   std::vector<float> inpL((size_t)N * d);
@@ -79,16 +83,17 @@ int decode(orc_ctx* ctx, const int32_t* tokens, int N, int n_past, int n_threads
     linear(ctx, cur.data(), N, d, m.get(p + "cross_attn.query.weight"), &m.get(p + "cross_attn.query.bias"), q.data(), n_threads);
     for (auto& x : q) x *= qk_scale;
     if (ctx->opt.act_f16_round) round_f16_inplace(q.data(), q.size());
-    std::vector<float> Kc((size_t)M * d), Vc((size_t)M * d);
-    {
-      const uint16_t* ks = ctx->cross_k.data() + (size_t)il * M * d;
-      const uint16_t* vs = ctx->cross_v.data() + (size_t)il * M * d;
-      for (size_t i = 0; i < Kc.size(); ++i) {
-        Kc[i] = f16_bits_to_f32(ks[i]);
-        Vc[i] = f16_bits_to_f32(vs[i]);
+    if (ctx->cross_kf.size() != ctx->cross_k.size()) {   // F16 -> f32 once per encode (encode clears the copies)
+      ctx->cross_kf.resize(ctx->cross_k.size());
+      ctx->cross_vf.resize(ctx->cross_v.size());
+      for (size_t i = 0; i < ctx->cross_k.size(); ++i) {
+        ctx->cross_kf[i] = f16_bits_to_f32(ctx->cross_k[i]);
+        ctx->cross_vf[i] = f16_bits_to_f32(ctx->cross_v[i]);
       }
     }
-    attention(ctx, q.data(), N, Kc.data(), Vc.data(), M, d, H, 1.0f, -1, att.data(), n_threads);
+    const float* Kc = ctx->cross_kf.data() + (size_t)il * M * d;
+    const float* Vc = ctx->cross_vf.data() + (size_t)il * M * d;
+    attention(ctx, q.data(), N, Kc, Vc, M, d, H, 1.0f, -1, att.data(), n_threads);
     linear(ctx, att.data(), N, d, m.get(p + "cross_attn.out.weight"), &m.get(p + "cross_attn.out.bias"), cur.data(), n_threads);
     for (size_t i = 0; i < inpFF.size(); ++i) inpFF[i] = cur[i] + inpCA[i];
     // D4: MLP
@@ -102,7 +107,7 @@ int decode(orc_ctx* ctx, const int32_t* tokens, int N, int n_past, int n_threads
   std::vector<float> last(d);
   layer_norm(inpL.data() + (size_t)(N - 1) * d, 1, d, m.get("decoder.ln.weight").f32(), m.get("decoder.ln.bias").f32(), last.data());
   ctx->logits.resize(n_vocab);
-  linear(ctx, last.data(), 1, d, m.get("decoder.token_embedding.weight"), nullptr, ctx->logits.data(), n_threads);
+  linear(ctx, last.data(), 1, d, m.get("decoder.token_embedding.weight"), nullptr, ctx->logits.data(), nt_all);
   return ORC_OK;
 }
 

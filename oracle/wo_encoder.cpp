@@ -168,6 +168,8 @@ int encode(orc_ctx* ctx, int n_threads, size_t mel_offset) {
   // E12: cross-attention memory (1990-2030)
   const int Lt = hp.n_text_layer;
   const int dt = hp.n_text_state;
+  ctx->cross_kf.clear();
+  ctx->cross_vf.clear();
   ctx->cross_k.assign((size_t)Lt * n_ctx * dt, 0);
   ctx->cross_v.assign((size_t)Lt * n_ctx * dt, 0);
   const float kscale = powf((float)d / (float)H, -0.25f);   // 1994

@@ -132,13 +132,19 @@ int load_model(const char* path, Model& m, std::string& err) {
   // is_multilingual (594-596) tests n_vocab == 51865 only; large-v3 carries 51866 and is
   // multilingual too, so the oracle generalises to >= 51865 -- an
   // oracle decision, since the reference would treat v3 as an English-only vocabulary.
+  // Every extra language token beyond the 99 of a 51865-entry vocabulary moves the ids behind the
+  // language block once more (upstream's dt = num_languages - 98 rule): large-v3's <|notimestamps|> is
+  // 50364 and its first time stamp 50365.
   if (m.vocab.n_vocab >= 51865) {                                             // 433-440
+    const int extra = m.vocab.n_vocab - 51865;
     m.vocab.token_eot += 1;
     m.vocab.token_sot += 1;
-    m.vocab.token_prev += 1;
-    m.vocab.token_solm += 1;
-    m.vocab.token_not += 1;
-    m.vocab.token_beg += 1;
+    m.vocab.token_prev += 1 + extra;
+    m.vocab.token_solm += 1 + extra;
+    m.vocab.token_not += 1 + extra;
+    m.vocab.token_beg += 1 + extra;
+    m.vocab.token_translate += extra;
+    m.vocab.token_transcribe += extra;
   }
   declare_tensors(m);
   // records until EOF (1384-1475; true EOF rather than the reference's fill_buf() < 12 test)

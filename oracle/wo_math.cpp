@@ -81,19 +81,38 @@ void gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc
              int K, int n_threads) {
   if (n_threads < 1) n_threads = 1;
   const int M2 = M & ~1, N4 = N & ~3;
-  parallel_for(M2 / 2, n_threads, [&](int ip) {
-    const int i = 2 * ip;
-    const float* a0 = A + (size_t)i * lda;
-    const float* a1 = a0 + lda;
-    float* c0 = C + (size_t)i * ldc;
-    float* c1 = c0 + ldc;
-    for (int j = 0; j < N4; j += 4) {
-      const float* b0 = B + (size_t)j * ldb;
-      micro_2x4(a0, a1, b0, b0 + ldb, b0 + 2 * (size_t)ldb, b0 + 3 * (size_t)ldb, K, c0 + j, c1 + j);
+  // cache blocking only: blocks of IB rows of A (one per worker at a time) x JB rows of B, sized so that a block
+  // pair (~(IB + JB) * K * 4 bytes) stays in a core's L2 while it is reused.  Every output element is still
+  // one micro_2x4 / dot1 over the whole K in the same order, so the results do not depend on the blocking.
+  const int IB = 32;
+  int JB = (int)((size_t)(768 * 1024) / ((size_t)K * 4)) & ~3;
+  if (JB < 16) JB = 16;
+  if (JB > 256) JB = 256;
+  const int n_ib = (M2 + IB - 1) / IB;
+  parallel_for(n_ib, n_threads, [&](int ib) {
+    const int i_lo = ib * IB, i_hi = std::min(M2, i_lo + IB);
+    for (int j_lo = 0; j_lo < N4; j_lo += JB) {
+      const int j_hi = std::min(N4, j_lo + JB);
+      for (int i = i_lo; i < i_hi; i += 2) {
+        const float* a0 = A + (size_t)i * lda;
+        const float* a1 = a0 + lda;
+        float* c0 = C + (size_t)i * ldc;
+        float* c1 = c0 + ldc;
+        for (int j = j_lo; j < j_hi; j += 4) {
+          const float* b0 = B + (size_t)j * ldb;
+          micro_2x4(a0, a1, b0, b0 + ldb, b0 + 2 * (size_t)ldb, b0 + 3 * (size_t)ldb, K, c0 + j, c1 + j);
+        }
+      }
     }
-    for (int j = N4; j < N; ++j) {
-      c0[j] = dot1(a0, B + (size_t)j * ldb, K);
-      c1[j] = dot1(a1, B + (size_t)j * ldb, K);
+    for (int i = i_lo; i < i_hi; i += 2) {
+      const float* a0 = A + (size_t)i * lda;
+      const float* a1 = a0 + lda;
+      float* c0 = C + (size_t)i * ldc;
+      float* c1 = c0 + ldc;
+      for (int j = N4; j < N; ++j) {
+        c0[j] = dot1(a0, B + (size_t)j * ldb, K);
+        c1[j] = dot1(a1, B + (size_t)j * ldb, K);
+      }
     }
   });
   if (M2 < M) {
@@ -138,12 +157,11 @@ void layer_norm(const float* x, int T, int d, const float* w, const float* b, fl
 void linear(const orc_ctx* ctx, const float* x, int T, int K, const Tensor& W, const Tensor* bias,
             float* y, int n_threads) {
   const int N = W.ne[1];
-  std::vector<float> wf;
-  W.to_f32(wf);
+  const float* wf = W.f32_rows();
   std::vector<float> xr((size_t)T * K);
   std::memcpy(xr.data(), x, xr.size() * 4);
   if (ctx->opt.act_f16_round && W.f16) round_f16_inplace(xr.data(), xr.size());
-  gemm_nt(xr.data(), K, wf.data(), K, y, N, T, N, K, n_threads);
+  gemm_nt(xr.data(), K, wf, K, y, N, T, N, K, n_threads);
   if (bias) {
     const float* bp = bias->f32();
     for (int t = 0; t < T; ++t) {

@@ -97,12 +97,7 @@ def test_attention(ctx, n_seg, T, H):
     rng = np.random.default_rng(T + H)
     qkv = rng.standard_normal((n_seg * T, 3 * H * 64)).astype(np.float16)
     ref = _attention_ref(qkv, n_seg, T, H)
-    for variant in ("0", "1"):          # attention.cu (default) and the single-score-buffer cut of attention4.cu
-        os.environ["WB_ATTN4"] = variant
-        try:
-            got = api.dbg_attention(ctx, qkv, n_seg, T, H).astype(np.float32)
-        finally:
-            os.environ.pop("WB_ATTN4", None)
-        assert np.isfinite(got).all(), variant
-        assert rel_l2(got, ref) < 3e-3, variant
-        assert np.abs(got - ref).max() < 2e-2, variant
+    got = api.dbg_attention(ctx, qkv, n_seg, T, H).astype(np.float32)
+    assert np.isfinite(got).all()
+    assert rel_l2(got, ref) < 3e-3
+    assert np.abs(got - ref).max() < 2e-2

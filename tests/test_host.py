@@ -99,3 +99,112 @@ def test_cabi_loader_errors_and_no_cpu_fallback(pkg, model_path, tmp_path):
         with pytest.raises(api.WsError) as e:
             api.WhisperContext.new(model_path("micro"))
         assert e.value.variant == "WrongGTensor" and "no CPU fallback" in str(e.value)
+
+
+def test_loader_wrong_size_and_wrong_bytes(pkg, model_path, tmp_path):
+    """WsError::WrongSizeTensor (src/main.rs:1406-1411: element count differs from the declared tensor) and
+    WsError::WrongBytesTensor (1428-1433: the record's ftype gives a byte size other than the declared dtype's),
+    through the C-ABI -- both are raised by the file parser, before any device is touched."""
+    from whisper_rs_b200 import api
+    mf = pkg.ggml_file.read_model(model_path("micro"))
+    d = mf.hparams.n_audio_state
+    t = dict(mf.tensors)
+    t["encoder.ln_post.weight"] = np.ones((d + 1,), np.float32)            # one element too many
+    p = tmp_path / "size.bin"
+    pkg.ggml_file.write_model(str(p), mf.hparams, 0, tensors=t)
+    with pytest.raises(api.WsError) as e:
+        api.WhisperContext.new(str(p))
+    assert e.value.variant == "WrongSizeTensor" and e.value.code == -7 and "wrong size" in str(e.value)
+    t = dict(mf.tensors)
+    w = "encoder.blocks.0.mlp.0.weight"
+    assert mf.hparams.f16 == 1 and t[w].dtype == np.float16
+    t[w] = t[w].astype(np.float32)                                          # right shape, ftype 0 where F16 is declared
+    p = tmp_path / "bytes.bin"
+    pkg.ggml_file.write_model(str(p), mf.hparams, 0, tensors=t)
+    with pytest.raises(api.WsError) as e:
+        api.WhisperContext.new(str(p))
+    assert e.value.variant == "WrongBytesTensor" and e.value.code == -9 and "wrong bytes" in str(e.value)
+    t = dict(mf.tensors)
+    t["encoder.ln_post.bias"] = t["encoder.ln_post.bias"].astype(np.float16)   # F16 where f32 is declared
+    p = tmp_path / "bytes2.bin"
+    pkg.ggml_file.write_model(str(p), mf.hparams, 0, tensors=t)
+    with pytest.raises(api.WsError) as e:
+        api.WhisperContext.new(str(p))
+    assert e.value.variant == "WrongBytesTensor"
+    # a tensor of the table that the file never fills (BadRefTensor, 66-67)
+    t = dict(mf.tensors)
+    del t["decoder.ln.bias"]
+    p = tmp_path / "missing.bin"
+    pkg.ggml_file.write_model(str(p), mf.hparams, 0, tensors=t)
+    with pytest.raises(api.WsError) as e:
+        api.WhisperContext.new(str(p))
+    assert e.value.variant == "BadRefTensor"
+    # truncated file: the last record's data is cut short
+    raw = open(model_path("micro"), "rb").read()
+    p = tmp_path / "short.bin"
+    p.write_bytes(raw[:-100])
+    with pytest.raises(api.WsError) as e:
+        api.WhisperContext.new(str(p))
+    assert e.value.variant == "UnexpectIO"
+
+
+def test_abi_struct_layout_matches_ctypes(pkg):
+    """A plain-C consumer of include/whisper_b200.h (tests/c/abi_layout.c, gcc -std=c99 -pedantic) prints the layout
+    the compiler gives every struct that crosses the ABI; the hand-written ctypes mirror must agree field by field
+    (a drift in wb_config / wb_timings would otherwise go unnoticed)."""
+    import subprocess
+    from whisper_rs_b200 import cabi
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+    subprocess.run(["make", "-C", cdir, "abi_layout"], check=True, stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(cdir, "abi_layout")], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for line in out.splitlines():
+        f = line.split()
+        got[f[0]] = tuple(int(x) for x in f[1:])
+    for name, st in (("wb_config", cabi.WbConfig), ("wb_timings", cabi.WbTimings)):
+        assert got[f"sizeof.{name}"] == (C.sizeof(st),), name
+        for fname, _ in st._fields_:
+            fld = getattr(st, fname)
+            assert got[f"{name}.{fname}"] == (fld.offset, fld.size), (name, fname)
+        assert len([k for k in got if k.startswith(name + ".")]) == len(st._fields_), name
+    assert got["enum.WB_ERR_TENSOR_OP"] == (cabi.WB_ERR_TENSOR_OP,)
+    assert got["enum.WB_STAGE_CROSS_V"] == (cabi.STAGE_CROSS_V,)
+    assert got["enum.WB_NORM_SEGMENT"] == (cabi.NORM_SEGMENT,)
+
+
+def test_main_replay_builds_and_fails_loudly_without_gpu(pkg, model_path, tmp_path):
+    """tests/c/main_replay.c -- the reference's `fn main` (src/main.rs:2065-2075) in C against the header -- links
+    against libwhisper_b200.so with gcc alone; without a B200 it exits with WsError::WrongGTensor (10), not a CPU
+    result."""
+    import subprocess
+    import torch
+    from whisper_rs_b200 import cabi
+    cabi.build()
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+    subprocess.run(["make", "-C", cdir, "main_replay"], check=True, stdout=subprocess.DEVNULL)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is tests/test_gpu_cabi.py")
+    pcm = tmp_path / "pcm.raw"
+    pkg.synth.make_segment(0, 160 * 64, 0.1).tofile(str(pcm))
+    r = subprocess.run([os.path.join(cdir, "main_replay"), model_path("micro"), str(pcm), str(tmp_path / "out")],
+                       capture_output=True, text=True)
+    assert r.returncode == 10 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_special_tokens_follow_the_language_count(pkg, pyoracle, tmp_path):
+    """Special-token fix-up (src/main.rs:433-440): +1 for a 51865-entry (multilingual) vocabulary; every further
+    language token (large-v3: 51866) moves the ids behind the language block once more -- <|notimestamps|> 50364,
+    first time stamp 50365, translate / transcribe 50359 / 50360 -- while eot / sot stay at 50257 / 50258."""
+    import dataclasses
+    micro = pkg.ggml_file.ARCHS["micro"]
+    want = {
+        51864: (50256, 50257, 50360, 50361, 50362, 50363, 50358, 50359),
+        51865: (50257, 50258, 50361, 50362, 50363, 50364, 50358, 50359),
+        51866: (50257, 50258, 50362, 50363, 50364, 50365, 50359, 50360),
+    }
+    for nv, ids in want.items():
+        p = str(tmp_path / f"v{nv}.bin")
+        pkg.ggml_file.write_model(p, dataclasses.replace(micro, n_vocab=nv), seed=1, n_vocab_file=50257)
+        o = pyoracle.Oracle(p)
+        assert (o.token_eot, o.token_sot, o.token_prev, o.token_solm, o.token_not, o.token_beg, o.token_translate,
+                o.token_transcribe) == ids, nv

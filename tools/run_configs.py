@@ -93,7 +93,17 @@ if __name__ == "__main__":
     ap.add_argument("--world", type=int, default=8)
     ap.add_argument("--windows", type=int, default=120)
     ap.add_argument("--max-new", type=int, default=224)
+    ap.add_argument("--only-load", default=None, help="create one context of this architecture (15 segments) and report the time")
     a = ap.parse_args()
+    if a.only_load:
+        path = model(a.only_load)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            ctx = api.WhisperContext.new(path, max_segments=15, max_clips=1, max_clip_samples=15 * 480000 + 240)
+            dt = time.perf_counter() - t0
+            print(json.dumps({"arch": a.only_load, "load_s": dt, "t_load_us": ctx.timings()["t_load_us"], "rep": rep}), flush=True)
+            ctx.close()
+        sys.exit(0)
     if "small" in a.which:
         print(json.dumps(config3()), flush=True)
     if "large-v3" in a.which:

@@ -54,7 +54,8 @@ class WhisperContext:
 
     def __init__(self, fname: str, max_segments: int = 1, max_clips: int = 1,
                  max_clip_samples: int = 480000, device: int = 0, checkpoints: bool = False,
-                 stream: Optional[int] = None, decode_capacity: bool = True, time_kernels: bool = False):
+                 stream: Optional[int] = None, decode_capacity: bool = True, time_kernels: bool = False,
+                 norm_scope: int = cabi.NORM_CLIP):
         L = cabi.lib()
         cfg = cabi.WbConfig()
         L.wb_config_default(C.byref(cfg))
@@ -63,6 +64,7 @@ class WhisperContext:
         cfg.max_clips = max_clips
         cfg.max_clip_samples = max_clip_samples
         cfg.checkpoints = int(checkpoints)
+        cfg.norm_scope = int(norm_scope)
         cfg.stream = stream
         cfg.decode_capacity = int(decode_capacity)
         cfg.reserved[0] = int(time_kernels)

@@ -23,6 +23,7 @@ _lib: Optional[C.CDLL] = None
  WB_ERR_BAD_REF_TENSOR, WB_ERR_WRONG_SIZE_TENSOR, WB_ERR_WRONG_SHAPE_TENSOR, WB_ERR_WRONG_BYTES_TENSOR,
  WB_ERR_TENSOR_OP) = (0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10)
 (STAGE_MEL, STAGE_CONV1, STAGE_CONV2_POS, STAGE_LAYER, STAGE_LN_POST, STAGE_CROSS_K, STAGE_CROSS_V) = range(7)
+NORM_CLIP, NORM_SEGMENT = 0, 1
 
 
 class WbConfig(C.Structure):

@@ -56,10 +56,13 @@ struct Gemm2Args {
   __half* vt_out;          // columns >= vt_col0 go to the transposed V buffer (see GemmEpilogue)
   int vt_col0, vt_heads, vt_head_rows, vt_ld, vt_T;
   // LayerNorm folded into the GEMMs around it (see the LN template parameter)
-  float2* ln_stats_out;        // LN == 1: per-row (sum, sum of squares) of the f32 output, accumulated atomically
-  __half* x16_out;             // LN == 1: F16 copy of the f32 output [row][x16_ld] (the next GEMM's A operand)
+  float2* ln_part_out;         // LN == 1: [row][ln_parts] partial (sum, sum of squares) of (x - center[row]), one slot
+                               //          per (N tile, epilogue half): plain stores, summed in slot order by the consumer
+  __half* x16_out;             // LN == 1: F16 copy of x - center[row], [row][x16_ld] (the next GEMM's A operand)
   int x16_ld;
-  const float2* ln_stats_in;   // LN == 2: the statistics of this GEMM's A rows
+  const float2* ln_part_in;    // LN == 2: the partial statistics of this GEMM's A rows
+  int ln_parts;                // partials per row
+  float* ln_center;            // [row] per-row centre: read by LN == 1, advanced by the row mean by LN == 2 (N tile 0)
   float ln_inv_d, ln_eps;
   long long* dbg;          // optional clock64() trace (CTA 0): [0,256) MMA warp, [256,1024) epilogue warp 4
 };
@@ -102,10 +105,15 @@ __device__ __forceinline__ Item item_coord(const Gemm2Args& a, int item) {
 // LN: LayerNorm (galois_norm + repeat/mul/add, src/main.rs:1781-1785, 1882-1886, 1948-1952) folded into the two
 // GEMMs around it, so the normalised activations never make a round trip through HBM:
 //   LN == 1 (producer, with RES): the epilogue that writes the f32 residual stream x also writes an F16 copy of
-//           it and accumulates each row's sum and sum of squares (thread = row: two atomics per thread per tile);
-//   LN == 2 (consumer): A is that F16 copy and W' = W diag(gamma); with mu, rstd from the row statistics
-//           LN(x) W^T + b = rstd * (x W'^T - mu * c1) + c2,  c1[n] = sum_k W'[n][k],  c2[n] = sum_k W[n][k] beta[k] + b[n]
-//           (c1 arrives in the column-scale slot, c2 in the bias slot).
+//           x - c, c = center[row] (the row's mean at the previous LayerNorm: the residual stream moves slowly, so
+//           x - c is nearly centred -- rounding x itself to F16 would lose the deviations of a row whose mean is
+//           large against its spread, and sum(x^2) - sum(x)^2 / d would cancel), and leaves the sum and the sum of
+//           squares of x - c over its share of the row in its own slot (thread = row; no atomics: the result
+//           does not depend on the order the tiles finish in);
+//   LN == 2 (consumer): A is that F16 copy and W' = W diag(gamma); the slots are added in slot order to mu' (the
+//           mean of x - c) and rstd, and
+//           LN(x) W^T + b = rstd * ((x - c) W'^T - mu' * c1) + c2,  c1[n] = sum_k W'[n][k],  c2[n] = sum_k W[n][k] beta[k] + b[n]
+//           (c1 arrives in the column-scale slot, c2 in the bias slot); the CTA of N tile 0 moves center[row] on by mu'.
 template <int BN, bool F16O, bool GELU, bool CS, bool RES, int LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
@@ -282,7 +290,16 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
       const int ln_m = m_row0 + lane;
       const long long ln_row = (long long)it.b * args.M_rows + ln_m;
       float2 ln_st = make_float2(0.0f, 0.0f);
-      if (LN == 2 && ln_m < args.M_rows) ln_st = __ldg(args.ln_stats_in + ln_row);
+      float ln_c = 0.0f;
+      if (LN == 2 && ln_m < args.M_rows) {   // partial sums in slot order
+        const float2* pp = args.ln_part_in + ln_row * args.ln_parts;
+        for (int p = 0; p < args.ln_parts; ++p) {
+          const float2 v = __ldcg(pp + p);   // written by the previous kernel: L2, not the read-only path
+          ln_st.x += v.x;
+          ln_st.y += v.y;
+        }
+      }
+      if (LN == 1 && ln_m < args.M_rows) ln_c = __ldcg(args.ln_center + ln_row);
       const bool tre = args.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
       G2_TRACE(tre, 256 + t * 16 + 0);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -306,7 +323,9 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
         const float var = fmaxf(ln_st.y * args.ln_inv_d - mu * mu, 0.0f);
         ln_rstd = rsqrtf(var + args.ln_eps);
         ln_nmr = -mu * ln_rstd;
+        if (it.nt == 0 && half == 0 && ln_m < args.M_rows) args.ln_center[ln_row] += mu;   // the next producer's centre
       }
+      const uint64_t ln_nc2 = f2_pack(-ln_c, -ln_c);
       const uint64_t ln_rstd2 = f2_pack(ln_rstd, ln_rstd), ln_nmr2 = f2_pack(ln_nmr, ln_nmr);
       uint64_t ln_s1p = 0, ln_s2p = 0;       // LN == 1: two-lane partial sums (FADD2 / FFMA2)
       if (my_nch == 0) {   // narrow tile: this warp has no chunk, but its arrival is counted
@@ -433,12 +452,15 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
             x.z += __uint_as_float(r0[4 * g + 2]); x.w += __uint_as_float(r0[4 * g + 3]);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
                          : "memory");
-            if (LN == 1) {   // statistics of the f32 values; their F16 copy replaces the accumulator registers
-              const uint64_t xa = f2_pack(x.x, x.y), xb = f2_pack(x.z, x.w);
+            if (LN == 1) {   // statistics of the centred f32 values; their F16 copy replaces the accumulator registers
+              const uint64_t xa = f2_add(f2_pack(x.x, x.y), ln_nc2), xb = f2_add(f2_pack(x.z, x.w), ln_nc2);
               ln_s1p = f2_add(ln_s1p, f2_add(xa, xb));
               ln_s2p = f2_fma(xa, xa, f2_fma(xb, xb, ln_s2p));
-              r0[2 * g] = pack_h2(x.x, x.y);
-              r0[2 * g + 1] = pack_h2(x.z, x.w);
+              float c0, c1, c2, c3;
+              f2_unpack(xa, c0, c1);
+              f2_unpack(xb, c2, c3);
+              r0[2 * g] = pack_h2(c0, c1);
+              r0[2 * g + 1] = pack_h2(c2, c3);
             }
           }
           if (LN == 1 && ln_m < args.M_rows) {   // 32 columns = 64 bytes of this row (two full sectors)
@@ -493,8 +515,7 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
         float a0, a1, b0, b1;
         f2_unpack(ln_s1p, a0, a1);
         f2_unpack(ln_s2p, b0, b1);
-        atomicAdd(&args.ln_stats_out[ln_row].x, ln_s1 + a0 + a1);
-        atomicAdd(&args.ln_stats_out[ln_row].y, ln_s2 + b0 + b1);
+        args.ln_part_out[ln_row * args.ln_parts + it.nt * 2 + half] = make_float2(ln_s1 + a0 + a1, ln_s2 + b0 + b1);
       }
     }
     if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the stores' reads
@@ -536,7 +557,7 @@ template <int BN>
 cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaStream_t st) {
   const bool f16 = a.out_f16 != 0, gelu = a.gelu != 0, cs = a.colscale != nullptr || a.scale != 1.0f, res = a.has_res != 0;
   if (f16 && res) return cudaErrorInvalidValue;
-  const int ln = a.ln_stats_out ? 1 : a.ln_stats_in ? 2 : 0;
+  const int ln = a.ln_part_out ? 1 : a.ln_part_in ? 2 : 0;
   if (ln == 1) {   // producer of the folded LayerNorm: f32 residual stream out
     if (f16 || !res || cs) return cudaErrorInvalidValue;
     return gelu ? launch_one<BN, false, true, false, true, 1>(g, a, grid, st)
@@ -605,10 +626,14 @@ cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
   a.vt_head_rows = g.epi.vt_head_rows;
   a.vt_ld = g.epi.vt_ld;
   a.vt_T = g.epi.vt_T;
-  a.ln_stats_out = g.epi.ln_stats_out;
+  a.ln_part_out = g.epi.ln_part_out;
   a.x16_out = g.epi.x16_out;
   a.x16_ld = g.epi.x16_ld;
-  a.ln_stats_in = g.epi.ln_stats_in;
+  a.ln_part_in = g.epi.ln_part_in;
+  a.ln_parts = g.epi.ln_parts;
+  a.ln_center = g.epi.ln_center;
+  if (a.ln_part_out && a.ln_parts != 2 * a.n_tiles) return cudaErrorInvalidValue;   // one slot per (N tile, epilogue half)
+  if ((a.ln_part_out || a.ln_part_in) && (!a.ln_center || a.ln_parts < 1)) return cudaErrorInvalidValue;
   a.ln_inv_d = g.K > 0 ? 1.0f / (float)g.K : 0.0f;
   a.ln_eps = g.epi.ln_eps;
   a.dbg = g.dbg;

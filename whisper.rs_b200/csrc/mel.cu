@@ -289,6 +289,27 @@ __global__ void mel_normalize_kernel(float* __restrict__ mel, size_t per_clip, c
   }
 }
 
+// WB_NORM_SEGMENT: the maximum of one encoder window of a clip's log10 mel (frames past the clip end do not count:
+// they are zero-filled after normalisation).  grid (chunks, n_seg); seg_max_enc starts at enc(-1e20).
+__global__ void __launch_bounds__(256)
+mel_window_max_kernel(const float* __restrict__ mel, int n_mel, int n_len, const int* __restrict__ clip_ids,
+                      const long long* __restrict__ offsets, int Tm, int* __restrict__ seg_max_enc) {
+  const int seg = blockIdx.y;
+  const float* src = mel + (size_t)(clip_ids ? clip_ids[seg] : 0) * n_mel * n_len;
+  const long long off = offsets ? offsets[seg] : 0;
+  const long long n_in = min((long long)Tm, (long long)n_len - off);   // frames of the window inside the clip
+  float m = -INFINITY;
+  if (n_in > 0) {
+    const long long total = (long long)n_mel * n_in;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long j = i / n_in, t = i - j * n_in;
+      m = fmaxf(m, src[(size_t)j * n_len + off + t]);
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomicMax(&seg_max_enc[seg], enc_ordered(m));
+}
+
 __global__ void fill_i32_kernel(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -333,6 +354,13 @@ cudaError_t launch_mel_normalize(float* mel, int n_clips, size_t per_clip, const
   if (bx > 592) bx = 592;   // 4 x 148 SMs, grid-stride
   if (bx < 1) bx = 1;
   mel_normalize_kernel<<<dim3(bx, n_clips), 256, 0, st>>>(mel, per_clip, clip_max_enc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mel_window_max(const float* mel, int n_mel, int n_len, const int* clip_ids, const long long* offsets,
+                                  int n_seg, int Tm, int* seg_max_enc, cudaStream_t st) {
+  if (n_seg <= 0) return cudaSuccess;
+  mel_window_max_kernel<<<dim3(32, n_seg), 256, 0, st>>>(mel, n_mel, n_len, clip_ids, offsets, Tm, seg_max_enc);
   return cudaGetLastError();
 }
 

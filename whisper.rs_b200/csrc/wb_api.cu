@@ -177,15 +177,7 @@ void resolve_kernel_clocks(wb_ctx* ctx) {
   ctx->pending_events.clear();
 }
 
-// WB_ATTN4=1 (read at every call): the single-score-buffer attention kernel of attention4.cu (three CTAs per SM)
-// instead of attention.cu (two CTAs per SM, double-buffered scores).  Measured equal or slower; kept selectable.
-static bool use_attn4() {
-  const char* e = getenv("WB_ATTN4");
-  return e && e[0] == '1';
-}
-static cudaError_t run_attention(const AttnProblem& ap, cudaStream_t st) {
-  return (use_attn4() && ap.has_map64) ? launch_attention4(ap, st) : launch_attention(ap, st);
-}
+static cudaError_t run_attention(const AttnProblem& ap, cudaStream_t st) { return launch_attention(ap, st); }
 
 static bool force_gemm1() {
   static const bool v = getenv("WB_GEMM1") != nullptr;   // developer aid: A/B the single-CTA kernel
@@ -204,12 +196,12 @@ int run_gemm(wb_ctx* ctx, const CUtensorMap& a_map, int M_rows, int batch, const
   g.N = l.N;
   g.K = l.K;
   if (!epi.bias) epi.bias = l.bias;
-  if (!epi.colscale) epi.colscale = epi.ln_stats_in ? l.ln_c1 : l.colscale;   // LN == 2 reads c1 from the column-scale slot
+  if (!epi.colscale) epi.colscale = epi.ln_part_in ? l.ln_c1 : l.colscale;   // LN == 2 reads c1 from the column-scale slot
   g.epi = epi;
   // pair kernel: needs the output (and residual) tensor maps; a residual needs whole tiles of f32 output
   const bool pair = out_map && l.bn2 && !epi.transpose_out && !force_gemm1() && (!epi.residual || res_map) &&
                     (!res_map || (!epi.out_f16 && l.N % l.bn2 == 0 && epi.vt_col0 >= l.N));
-  if ((epi.ln_stats_out || epi.ln_stats_in) && !pair)
+  if ((epi.ln_part_out || epi.ln_part_in) && !pair)
     return fail_msg(ctx, WB_ERR_TENSOR_OP, "galois tensor:'LayerNorm-folded GEMM needs the pair kernel'");
   LaunchTimer t(ctx, family);
   if (pair) {
@@ -516,7 +508,15 @@ int alloc_activations(wb_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->h1, S * (Tm + 2) * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->x, S * T * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->ln_out, S * T * d))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->ln_stats, S * T * 2 * (size_t)hp.n_audio_layer + 1))) return rc;
+  if (ctx->ln_fold) {
+    ctx->ln_parts = 2 * ((int)d / gemm2_pick_bn((int)d));
+    for (int i = 0; i < 2; ++i)
+      if ((rc = dev_alloc(ctx, &ctx->ln_part[i], S * T * (size_t)ctx->ln_parts))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ln_center, S * T))) return rc;
+    std::vector<float> ones(d, 1.0f), zeros(d, 0.0f);
+    if ((rc = upload_f32_vec(ctx, ones, &ctx->enc_ones))) return rc;
+    if ((rc = upload_f32_vec(ctx, zeros, &ctx->enc_zeros))) return rc;
+  }
   if ((rc = dev_alloc(ctx, &ctx->qk, S * T * 2 * d))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vt, S * (d / 64) * ATTN_VT_HEAD_ROWS * ctx->Tp))) return rc;
   WB_CK(launch_vt_init(ctx->vt, (int)(S * (d / 64)), ctx->Tp, ctx->stream));
@@ -529,6 +529,11 @@ int alloc_activations(wb_ctx* ctx) {
   ctx->n_chk_slots = 4 + hp.n_audio_layer + 2 * hp.n_text_layer;
   if ((rc = dev_alloc(ctx, &ctx->d_chk, (size_t)ctx->n_chk_slots * S))) return rc;
   ctx->chk_valid.assign(ctx->n_chk_slots, 0);
+  {
+    uint8_t* scratch = nullptr;
+    if ((rc = dev_alloc(ctx, &scratch, abs_sum_scratch_bytes((int)S)))) return rc;   // zeroed: the arrival counters start at 0
+    ctx->d_chk_scratch = scratch;
+  }
   // mel buffers
   const size_t max_len = (size_t)(ctx->cfg.max_clip_samples / 160);
   ctx->d_mel_floats = (size_t)ctx->cfg.max_clips * ctx->mel_tab.n_mel * (max_len ? max_len : 1);
@@ -550,6 +555,7 @@ int alloc_activations(wb_ctx* ctx) {
   WB_CK(cudaHostAlloc((void**)&ctx->h_offsets, sizeof(long long) * WB_N_TICKETS * ctx->cfg.max_segments, cudaHostAllocDefault));
   WB_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if ((rc = dev_alloc(ctx, &ctx->d_clip_max, (size_t)ctx->cfg.max_clips))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_seg_max, S))) return rc;
   return WB_OK;
 }
 
@@ -617,8 +623,8 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
     return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: n_audio_state != n_text_state");
   if (hp.n_audio_state % 64 != 0 || hp.n_audio_state > 1280 || hp.n_mels % 8 != 0 || mv.filt_n_mel != hp.n_mels)
     return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: unsupported model dimensions");
-  if (cfg.norm_scope != WB_NORM_CLIP)
-    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: only the whole-clip normalisation scope of the reference is implemented");
+  if (cfg.norm_scope != WB_NORM_CLIP && cfg.norm_scope != WB_NORM_SEGMENT)
+    return fail_msg(nullptr, WB_ERR_UNEXPECTED, "Unexpected: norm_scope must be WB_NORM_CLIP or WB_NORM_SEGMENT");
 
   // ---- device: no CPU fallback
   int n_dev = 0;
@@ -659,8 +665,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
   const char* aerr = "";
-  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr) ||
-      !attention4_setup_attributes(&aerr)) {
+  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
     fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'kernel attribute setup: ") + aerr + "'");
     return bail(WB_ERR_TENSOR_OP);
   }
@@ -827,21 +832,33 @@ static int mel_logmel(wb_ctx* ctx, const void* pcm_dev, int is_i16, size_t n_sam
   ctx->mel_n_len = (int)n_len;
   ctx->mel_n_clips = n_clips;
   ctx->mel_normalized = false;
+  ctx->mel_materialized = false;
   return WB_OK;
 }
 
-// stage 2: clamp_and_normalize (1654-1671) with the maxima in d_clip_max
+// clamp_and_normalize (1654-1671) of the stored mel in place, with the maxima in d_clip_max
+static int mel_materialize(wb_ctx* ctx) {
+  if (ctx->mel_materialized || ctx->cfg.norm_scope != WB_NORM_CLIP) return WB_OK;
+  LaunchTimer t(ctx, "mel_normalize");
+  WB_CK(launch_mel_normalize(ctx->d_mel, ctx->mel_n_clips, (size_t)ctx->mel_tab.n_mel * (size_t)ctx->mel_n_len, ctx->d_clip_max,
+                             ctx->stream));
+  ctx->mel_materialized = true;
+  return WB_OK;
+}
+
+// stage 2: clamp_and_normalize (1654-1671) with the maxima in d_clip_max.  The maxima are final from here on; the
+// two f32 operations themselves run inside the encoder's window copy (mel_window_kernel), which reads every mel
+// value anyway -- the stored mel is rewritten in place only when somebody looks at it (wb_mel_read, checkpoints).
 static int mel_norm(wb_ctx* ctx) {
   const int n_mel = ctx->mel_tab.n_mel, n_clips = ctx->mel_n_clips;
   const size_t n_len = (size_t)ctx->mel_n_len;
-  {
-    LaunchTimer t(ctx, "mel_normalize");
-    WB_CK(launch_mel_normalize(ctx->d_mel, n_clips, (size_t)n_mel * n_len, ctx->d_clip_max, ctx->stream));
-  }
   ctx->mel_normalized = true;
   if (ctx->cfg.checkpoints) {
+    int rc = mel_materialize(ctx);
+    if (rc) return rc;
     WB_CK(launch_abs_sum_f32(ctx->d_mel, (long long)n_mel * n_len, (long long)n_mel * n_len,
-                             n_clips < ctx->cfg.max_segments ? n_clips : ctx->cfg.max_segments, ctx->d_chk, ctx->stream));
+                             n_clips < ctx->cfg.max_segments ? n_clips : ctx->cfg.max_segments, ctx->d_chk, ctx->d_chk_scratch,
+                             ctx->cfg.max_segments, ctx->stream));
     ctx->chk_valid[0] = 1;
   }
   cudaEventRecord(ctx->ev[0][1], ctx->stream);
@@ -872,6 +889,10 @@ static int stage_host_pcm(wb_ctx* ctx, const void* pcm, size_t bytes) {
     ctx->pf_host[other] = nullptr;
     WB_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[other], 0));
   } else {
+    // a prefetch that is not consumed by the very next upload is dropped: matching a LATER call by pointer
+    // identity would run the mel on whatever the buffer held when it was prefetched
+    ctx->pf_host[other] = nullptr;
+    ctx->pf_bytes[other] = 0;
     WB_CK(cudaMemcpyAsync(ctx->d_pcm_buf[ctx->pcm_cur], pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   ctx->d_pcm = ctx->d_pcm_buf[ctx->pcm_cur];
@@ -961,6 +982,10 @@ int wb_mel_read(wb_ctx* ctx, int clip, float* out, size_t cap_floats) {
   cudaSetDevice(ctx->device);
   const size_t n = (size_t)ctx->mel_tab.n_mel * ctx->mel_n_len;
   if (cap_floats < n) return fail_msg(ctx, WB_ERR_NOT_ENOUGH_SPACE, "not enough space in the context's memory pool\n");
+  if (ctx->mel_normalized) {   // ctx.mel holds normalised values in the reference (1648): apply them now if still pending
+    int rc = mel_materialize(ctx);
+    if (rc) return rc;
+  }
   WB_CK(cudaMemcpyAsync(out, ctx->d_mel + (size_t)clip * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
   return WB_OK;
@@ -976,6 +1001,7 @@ int wb_mel_write(wb_ctx* ctx, const float* mel, int n_mel, int n_len, int n_clip
   ctx->mel_n_len = n_len;
   ctx->mel_n_clips = n_clips;
   ctx->mel_normalized = true;
+  ctx->mel_materialized = true;   // the caller's values are used as they are
   return WB_OK;
 }
 
@@ -1044,15 +1070,6 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     const uint64_t strd[1] = {(uint64_t)ctx->Tp * 2};
     const uint32_t box[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
     ok = make_tmap_f16(&ap.vt_map, ctx->vt, 2, dims, strd, box, &terr);
-    const uint32_t box64[2] = {64, 64};
-    ok = ok && make_tmap_f16(&ap.vt_map64, ctx->vt, 2, dims, strd, box64, &terr);
-  }
-  if (ok) {
-    const uint64_t dims[4] = {64, (uint64_t)2 * H, (uint64_t)T, (uint64_t)n_seg};
-    const uint64_t strd[3] = {128, (uint64_t)2 * d * 2, (uint64_t)T * 2 * d * 2};
-    const uint32_t box64[4] = {64, 1, 64, 1};
-    ok = make_tmap_f16(&ap.qk_map64, ctx->qk, 4, dims, strd, box64, &terr);
-    ap.has_map64 = ok;
   }
   // epilogue output / residual boxes of the pair GEMM
   ok = ok && tmap_out(&o_conv1, ctx->h1 + d, false, d, Tm, n_seg, d, (uint64_t)(Tm + 2) * d, &terr) &&
@@ -1073,24 +1090,42 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   }
 
   auto probe_f32 = [&](int slot, const float* p, long long per_seg, long long seg_stride) -> int {
-    WB_CK(launch_abs_sum_f32(p, per_seg, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, st));
+    WB_CK(launch_abs_sum_f32(p, per_seg, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, ctx->d_chk_scratch,
+                             ctx->cfg.max_segments, st));
     ctx->chk_valid[slot] = 1;
     return WB_OK;
   };
   auto probe_f16 = [&](int slot, const __half* p, int rows, int cols, long long row_stride, long long seg_stride) -> int {
-    WB_CK(launch_abs_sum_f16(p, rows, cols, row_stride, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, st));
+    WB_CK(launch_abs_sum_f16(p, rows, cols, row_stride, seg_stride, n_seg, ctx->d_chk + (size_t)slot * ctx->cfg.max_segments, ctx->d_chk_scratch,
+                             ctx->cfg.max_segments, st));
     ctx->chk_valid[slot] = 1;
     return WB_OK;
   };
   int rc;
+  // conv_in and h1 hold [(Tm + 2) rows] per segment with zero rows 0 and Tm + 1 (the convolutions' padding); the
+  // kernels only ever write rows 1 .. Tm.  When the audio context changes the pad rows move onto memory that held
+  // activations of the previous layout, so both buffers are cleared once per change of T.
+  if (ctx->pad_T != T) {
+    const size_t S = (size_t)ctx->cfg.max_segments, Tm_max = 2 * (size_t)hp.n_audio_ctx;
+    WB_CK(cudaMemsetAsync(ctx->conv_in, 0, S * (Tm_max + 2) * n_mels * sizeof(__half), st));
+    WB_CK(cudaMemsetAsync(ctx->h1, 0, S * (Tm_max + 2) * d * sizeof(__half), st));
+    ctx->pad_T = T;
+  }
   const bool fold = ctx->ln_fold;
-  const size_t ln_stride = (size_t)ctx->cfg.max_segments * T;   // rows per statistics slot
-  if (fold && L > 0) WB_CK(cudaMemsetAsync(ctx->ln_stats, 0, sizeof(float2) * ln_stride * 2 * L, st));
 
   // E0: mel window -> token-major F16 rows with zero padding rows (1816-1829)
+  // fused with clamp_and_normalize (1654-1671) when the stored mel still holds log10 values: with the clip's maximum
+  // (WB_NORM_CLIP, the reference) or the window's own (WB_NORM_SEGMENT)
+  const int norm_mode = ctx->mel_materialized ? 0 : ctx->cfg.norm_scope == WB_NORM_SEGMENT ? 2 : 1;
+  if (norm_mode == 2) {
+    LaunchTimer t(ctx, "mel_window_max");
+    WB_CK(launch_fill_i32(ctx->d_seg_max, n_seg, mel_enc_ordered_host(-1e20f), st));
+    WB_CK(launch_mel_window_max(ctx->d_mel, n_mels, ctx->mel_n_len, ctx->d_clip_ids, ctx->d_offsets, n_seg, Tm, ctx->d_seg_max, st));
+  }
   {
     LaunchTimer t(ctx, "mel_window");
-    WB_CK(launch_mel_window(ctx->d_mel, n_mels, ctx->mel_n_len, ctx->d_clip_ids, ctx->d_offsets, n_seg, Tm, ctx->conv_in, st));
+    WB_CK(launch_mel_window(ctx->d_mel, n_mels, ctx->mel_n_len, ctx->d_clip_ids, ctx->d_offsets, n_seg, Tm, ctx->conv_in, st,
+                            norm_mode == 2 ? ctx->d_seg_max : ctx->d_clip_max, norm_mode));
   }
   // E1: conv1 + bias + GELU (1834-1855) as an implicit GEMM: row t = input rows t-1, t, t+1
   {
@@ -1114,11 +1149,6 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     e.out_f16 = 0;
     e.out_bstride = (long long)T * d;
     e.out_ld = d;
-    if (fold && L > 0) {   // feeds attn_ln of layer 0
-      e.ln_stats_out = ctx->ln_stats;
-      e.x16_out = ctx->ln_out;
-      e.x16_ld = d;
-    }
     if ((rc = run_gemm(ctx, m_conv2, T, n_seg, ctx->conv2, e, "gemm_conv2", &o_x3, &o_pe, 1))) return rc;
     if (chk && (rc = probe_f32(2, ctx->x, (long long)T * d, (long long)T * d))) return rc;
   }
@@ -1127,6 +1157,12 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     if (!fold) {   // E4: attn_ln
       LaunchTimer t(ctx, "layernorm");
       WB_CK(launch_layernorm(ctx->x, l.attn_ln_w, l.attn_ln_b, M, d, ctx->ln_out, nullptr, st, 0, true));
+    } else if (il == 0) {
+      // folded: layer 0's attn_ln is the one LayerNorm that still runs as a kernel (gamma / beta are in the QKV
+      // weights, so plain normalisation): it gives every row the centre the folded LayerNorms downstream
+      // start from -- the producers round x - centre to F16, not x
+      LaunchTimer t(ctx, "layernorm");
+      WB_CK(launch_layernorm(ctx->x, ctx->enc_ones, ctx->enc_zeros, M, d, ctx->ln_out, nullptr, st, 0, true, ctx->ln_center));
     }
     {   // E5 + E6: fused Q|K|V projection, F16 repack; V transposed, time contiguous (1891-1920)
       GemmEpilogue e;
@@ -1139,7 +1175,11 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.vt_head_rows = ATTN_VT_HEAD_ROWS;
       e.vt_ld = ctx->Tp;
       e.vt_T = T;
-      if (fold) e.ln_stats_in = ctx->ln_stats + (size_t)(2 * il) * ln_stride;
+      if (fold && il > 0) {   // statistics left by the previous layer's fc2
+        e.ln_part_in = ctx->ln_part[0];
+        e.ln_parts = ctx->ln_parts;
+        e.ln_center = ctx->ln_center;
+      }
       if ((rc = run_gemm(ctx, m_ln, M, 1, l.qkv, e, "gemm_qkv", &o_qk))) return rc;
     }
     {   // E7: flash attention + head merge (1922-1929)
@@ -1154,7 +1194,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out_f16 = 0;
       e.out_ld = d;
       if (fold) {   // feeds mlp_ln
-        e.ln_stats_out = ctx->ln_stats + (size_t)(2 * il + 1) * ln_stride;
+        e.ln_part_out = ctx->ln_part[1];
+        e.ln_parts = ctx->ln_parts;
+        e.ln_center = ctx->ln_center;
         e.x16_out = ctx->ln_out;
         e.x16_ld = d;
       }
@@ -1170,7 +1212,11 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out = ctx->hidden;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
-      if (fold) e.ln_stats_in = ctx->ln_stats + (size_t)(2 * il + 1) * ln_stride;
+      if (fold) {
+        e.ln_part_in = ctx->ln_part[1];
+        e.ln_parts = ctx->ln_parts;
+        e.ln_center = ctx->ln_center;
+      }
       if ((rc = run_gemm(ctx, m_ln, M, 1, l.fc1, e, "gemm_fc1", &o_hid))) return rc;
     }
     {
@@ -1181,7 +1227,9 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
       e.out_f16 = 0;
       e.out_ld = d;
       if (fold && il + 1 < L) {   // feeds attn_ln of the next layer (ln_post keeps its own kernel: it has an f32 output)
-        e.ln_stats_out = ctx->ln_stats + (size_t)(2 * il + 2) * ln_stride;
+        e.ln_part_out = ctx->ln_part[0];
+        e.ln_parts = ctx->ln_parts;
+        e.ln_center = ctx->ln_center;
         e.x16_out = ctx->ln_out;
         e.x16_ld = d;
       }
@@ -1267,7 +1315,7 @@ int wb_encoder_digest(wb_ctx* ctx, double* out, int cap) {
   double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
   {
     LaunchTimer t(ctx, "digest");
-    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->stream));
+    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->d_chk_scratch, ctx->cfg.max_segments, ctx->stream));
   }
   WB_CK(cudaMemcpyAsync(out, slot, sizeof(double) * ctx->enc_n_seg, cudaMemcpyDeviceToHost, ctx->stream));
   WB_CK(cudaStreamSynchronize(ctx->stream));
@@ -1283,7 +1331,7 @@ int wb_encoder_digest_async(wb_ctx* ctx, double* out, int cap) {
   double* slot = ctx->d_chk + (size_t)(3 + ctx->hp.n_audio_layer) * ctx->cfg.max_segments;   // the LN_POST slot
   {
     LaunchTimer t(ctx, "digest");
-    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->stream));
+    WB_CK(launch_abs_sum_f32(ctx->enc_out, n, n, ctx->enc_n_seg, slot, ctx->d_chk_scratch, ctx->cfg.max_segments, ctx->stream));
   }
   WB_CK(cudaMemcpyAsync(out, slot, sizeof(double) * ctx->enc_n_seg, cudaMemcpyDeviceToHost, ctx->stream));
   const int ticket = ctx->ticket_next;
@@ -1473,12 +1521,8 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
     const uint64_t dims2[2] = {(uint64_t)Tp, (uint64_t)n_seg * H * ATTN_VT_HEAD_ROWS};
     const uint64_t strd2[1] = {(uint64_t)Tp * 2};
     const uint32_t box2[2] = {64, (uint32_t)ATTN_VT_HEAD_ROWS};
-    const uint32_t box64[4] = {64, 1, 64, 1}, box264[2] = {64, 64};
-    ap.has_map64 = true;
     if (!make_tmap_f16(&ap.qk_map, dQK, 4, dims, strd, box, &terr) ||
-        !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr) ||
-        !make_tmap_f16(&ap.qk_map64, dQK, 4, dims, strd, box64, &terr) ||
-        !make_tmap_f16(&ap.vt_map64, dVt, 2, dims2, strd2, box264, &terr)) {
+        !make_tmap_f16(&ap.vt_map, dVt, 2, dims2, strd2, box2, &terr)) {
       fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'") + terr + "'");
       cleanup();
       return WB_ERR_TENSOR_OP;

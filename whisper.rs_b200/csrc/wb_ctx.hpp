@@ -103,6 +103,9 @@ struct wb_ctx {
   int* d_clip_max = nullptr;
   int mel_n_len = 0, mel_n_clips = 0;
   bool mel_normalized = false;        // false between wb_pcm_to_logmel and wb_mel_normalize
+  bool mel_materialized = false;      // d_mel holds normalised values (after a read-back / wb_mel_write / checkpoints);
+                                      // otherwise log10 values, normalised on the way into the encoder's window copy
+  int* d_seg_max = nullptr;           // [max_segments] per-window maxima (WB_NORM_SEGMENT)
 
   // ---- encoder activations (capacity = cfg.max_segments)
   int* d_clip_ids = nullptr;
@@ -116,7 +119,11 @@ struct wb_ctx {
   float* x = nullptr;                 // residual stream [seg*T][d] f32
   __half* ln_out = nullptr;           // [seg*T][d]: LayerNorm output, or (ln_fold) the F16 copy of x
   bool ln_fold = false;               // attn_ln / mlp_ln folded into the GEMMs around them (gemm2.cu LN template)
-  float2* ln_stats = nullptr;         // [2 L][max_segments*T] per-row (sum, sum of squares) of x, one slot per LN
+  float2* ln_part[2] = {nullptr, nullptr};   // [max_segments*T][ln_parts] partial (sum, sum of squares) of x - centre, one
+                                      // slot per (N tile, epilogue half) of the producing GEMM; two buffers in alternation
+  float* ln_center = nullptr;         // [max_segments*T] per-row centre of the folded LayerNorms (gemm2.cu)
+  int ln_parts = 0;                   // 2 * (d / pair tile width)
+  const float *enc_ones = nullptr, *enc_zeros = nullptr;   // identity affine of layer 0's attn_ln (its gamma / beta live in the QKV weights)
   __half* qk = nullptr;               // [seg*T][2d]
   __half* vt = nullptr;               // [seg][H*64][Tp]
   __half* attn_out = nullptr;         // [seg*T][d]
@@ -131,7 +138,9 @@ struct wb_ctx {
   int enc_n_seg = 0;                  // segments of the last wb_encode
   int exp_n_audio_ctx = 0;            // exp_n_audio_ctx (src/main.rs:362): > 0 shortens the encoder's audio context
   int enc_T = 0;                      // audio context the last wb_encode ran with (rows per segment of its outputs)
+  int pad_T = 0;                      // audio context the zero pad rows of conv_in / h1 are laid out for (0 = as allocated)
   double* d_chk = nullptr;            // [slot][max_segments]
+  void* d_chk_scratch = nullptr;      // per-block partial sums + arrival counters of the sum|x| kernels (misc.cu)
   int n_chk_slots = 0;
   std::vector<char> chk_valid;
 
@@ -154,6 +163,7 @@ struct wb_ctx {
   float2* dec_ln_stats = nullptr;                // [3 Lt + 1][DEC_LN_ROWS] row statistics of the folded single-token step
   cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
   int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;
+  int step_graph_enc_T = 0, step_graph_n_split = 0;   // host parameters decode_pass bakes into the captured launches
 
   // ---- results read back without blocking (wb_encoder_digest_async / wb_wait)
   cudaEvent_t ev_ticket[WB_N_TICKETS] = {};

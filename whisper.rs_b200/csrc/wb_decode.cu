@@ -398,6 +398,9 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   if (rc) return rc;
   const ModelHParams& hp = ctx->hp;
   const int n_ctx = hp.n_text_ctx;
+  // the caller's arrays are [n_seqs][max_new]; the device-side ones are [n_seqs][min(max_new, n_text_ctx)] --
+  // only the step count is clamped, the caller's row stride is kept (2-D copies at the end)
+  const int out_stride = max_new;
   if (max_new > n_ctx) max_new = n_ctx;
   cudaStream_t st = ctx->stream;
   std::vector<int> toks((size_t)n_seqs * n_prompt);
@@ -426,8 +429,13 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   int n_past = n_prompt;
   const int n_steps_max = max_new - 1;
   const bool use_graph = !ctx->time_kernels;
+  // everything decode_pass bakes into its launches is part of the key: the audio context of the last encode (the
+  // segment stride of the cross K/V and the key-range split of the cross-attention) as well as the batch shape
+  const int enc_T = ctx->enc_T > 0 ? ctx->enc_T : hp.n_audio_ctx;
+  const int n_split = decode_cross_splits(n_seqs, hp.n_text_head, enc_T, ctx->num_sms);
   if (use_graph && (ctx->step_graph == nullptr || ctx->step_graph_n_seq != n_seqs ||
-                    ctx->step_graph_max_new != max_new || ctx->step_graph_eot != eot)) {
+                    ctx->step_graph_max_new != max_new || ctx->step_graph_eot != eot ||
+                    ctx->step_graph_enc_T != enc_T || ctx->step_graph_n_split != n_split)) {
     if (ctx->step_graph) {
       cudaGraphExecDestroy(ctx->step_graph);
       ctx->step_graph = nullptr;
@@ -451,6 +459,8 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     ctx->step_graph_n_seq = n_seqs;
     ctx->step_graph_max_new = max_new;
     ctx->step_graph_eot = eot;
+    ctx->step_graph_enc_T = enc_T;
+    ctx->step_graph_n_split = n_split;
   }
   std::vector<int> done_h(n_seqs, 0);
   for (int it = 0; it < n_steps_max; ++it) {
@@ -479,9 +489,11 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   ctx->ev_used[2] = true;
   ctx->dec_n_seq = n_seqs;
   ctx->tm.n_decode_calls += 1;
-  WB_CK(cudaMemcpyAsync(out_tokens, ctx->d_out_tokens, sizeof(int) * (size_t)n_seqs * max_new, cudaMemcpyDeviceToHost, st));
+  WB_CK(cudaMemcpy2DAsync(out_tokens, sizeof(int) * (size_t)out_stride, ctx->d_out_tokens, sizeof(int) * (size_t)max_new,
+                          sizeof(int) * (size_t)max_new, (size_t)n_seqs, cudaMemcpyDeviceToHost, st));
   if (out_margin)
-    WB_CK(cudaMemcpyAsync(out_margin, ctx->d_out_margin, sizeof(float) * (size_t)n_seqs * max_new, cudaMemcpyDeviceToHost, st));
+    WB_CK(cudaMemcpy2DAsync(out_margin, sizeof(float) * (size_t)out_stride, ctx->d_out_margin, sizeof(float) * (size_t)max_new,
+                            sizeof(float) * (size_t)max_new, (size_t)n_seqs, cudaMemcpyDeviceToHost, st));
   WB_CK(cudaMemcpyAsync(out_len, ctx->d_out_len, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, st));
   WB_CK(cudaStreamSynchronize(st));
   return WB_OK;

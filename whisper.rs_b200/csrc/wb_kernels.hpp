@@ -67,9 +67,15 @@ struct GemmEpilogue {
   int vt_ld = 0;
   int vt_T = 1;
   // LayerNorm folded into the GEMMs around it (pair kernel only, gemm2.cu): a producer (f32 residual-stream
-  // output) also writes an F16 copy x16_out[row*x16_ld + n] and accumulates per-row (sum, sum of squares) into
-  // ln_stats_out[row]; a consumer reads those statistics of its A rows (ln_stats_in, row width = K) and applies
-  // rstd * (acc - mu * colscale[n]) + bias[n].
+  // output) also writes an F16 copy of x - ln_center[row] to x16_out[row*x16_ld + n] and leaves the (sum, sum of
+  // squares) of x - center over its columns in ln_part_out[row*ln_parts + slot] (ln_parts = 2 * N tiles: plain
+  // stores, no atomics); a consumer adds the ln_parts slots of its A rows in slot order (ln_part_in, row width = K),
+  // applies rstd * (acc - mu' * colscale[n]) + bias[n] and moves ln_center[row] on by mu'.
+  float2* ln_part_out = nullptr;
+  const float2* ln_part_in = nullptr;
+  int ln_parts = 0;
+  float* ln_center = nullptr;
+  // the same fold in the decoder's single-token step (decode_kernels.cu): per-row (sum, sum of squares) of x
   float2* ln_stats_out = nullptr;
   __half* x16_out = nullptr;
   int x16_ld = 0;
@@ -106,17 +112,12 @@ constexpr int ATTN_VT_HEAD_ROWS = 80;   // 64 head rows + 1 row of ones + 15 zer
 struct AttnProblem {
   CUtensorMap qk_map;  // dims {64, 2H, T, B} over the [B*T][2d] Q|K buffer, box {64,1,128,1}
   CUtensorMap vt_map;  // dims {Tp, B*H*80} over V^T, box {64, 80}
-  CUtensorMap qk_map64;  // the same tensors with 64-row boxes ({64,1,64,1} / {64, 64}) for the 4-CTA-per-SM
-  CUtensorMap vt_map64;  // kernel (attention4.cu); valid when has_map64
-  bool has_map64 = false;
   int B = 0, T = 0, H = 0;
   __half* out = nullptr;  // [B*T][H*64] merged heads (1924-1929)
   float scale = 0.125f;
   long long* dbg = nullptr;  // optional clock64() trace buffer (1024 entries) for tools/prof_attention.py
 };
 cudaError_t launch_attention(const AttnProblem& a, cudaStream_t st);
-cudaError_t launch_attention4(const AttnProblem& a, cudaStream_t st);   // attention4.cu: four CTAs per SM
-bool attention4_setup_attributes(const char** err);
 cudaError_t launch_vt_init(__half* vt, int n_heads_total, int Tp, cudaStream_t st);   // ones / zero rows
 bool attention_setup_attributes(const char** err);
 
@@ -146,17 +147,25 @@ cudaError_t launch_fill_i32(int* p, int n, int v, cudaStream_t st);
 // ---- small fused kernels -------------------------------------------------------------------------
 // E0 (1816-1829) + F16 rounding of the conv operand: [clip][n_mel][n_len] f32 window ->
 // [seg][Tm + 2][n_mel] f16 token-major with one zero row before and after.
+// norm_mode 0: the mel is already normalised; 1 / 2: it holds log10 values and clamp_and_normalize (1654-1671) is
+// applied on the way through with the maximum max_enc[clip] / max_enc[seg] (ordered-int encoding, mel.cu)
 cudaError_t launch_mel_window(const float* mel, int n_mel, int n_len, const int* clip_ids,
-                              const long long* offsets, int n_seg, int Tm, __half* out, cudaStream_t st);
+                              const long long* offsets, int n_seg, int Tm, __half* out, cudaStream_t st,
+                              const int* max_enc = nullptr, int norm_mode = 0);
+// per-segment maximum of the window [offset, offset + Tm) of its clip's log10 mel (WB_NORM_SEGMENT)
+cudaError_t launch_mel_window_max(const float* mel, int n_mel, int n_len, const int* clip_ids, const long long* offsets,
+                                  int n_seg, int Tm, int* seg_max_enc, cudaStream_t st);
 // galois_norm + repeat/mul/add (1781-1785, 1882-1886): rows of d, f32 in; f16 and/or f32 out
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, int rows, int d,
                              __half* out_f16, float* out_f32, cudaStream_t st, long long in_row_stride = 0,
-                             bool pdl = false);
-// sum|x| probes (1836-1849): out[seg] = sum over that segment's elements
+                             bool pdl = false, float* center_out = nullptr);   // center_out[row] = the row's mean
+// sum|x| probes (1836-1849): out[seg] = sum over that segment's elements, bit-reproducible (per-block partial
+// slots added in slot order by the last block).  `scratch`: abs_sum_scratch_bytes(scratch_segs) zero-initialised bytes.
+size_t abs_sum_scratch_bytes(int max_seg);
 cudaError_t launch_abs_sum_f32(const float* x, long long per_seg, long long seg_stride, int n_seg, double* out,
-                               cudaStream_t st);
+                               void* scratch, int scratch_segs, cudaStream_t st);
 cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long row_stride, long long seg_stride,
-                               int n_seg, double* out, cudaStream_t st);
+                               int n_seg, double* out, void* scratch, int scratch_segs, cudaStream_t st);
 
 // ---- decoder step kernels (absent in the reference) ------------------------
 // n_past / step live in device memory so one captured CUDA graph serves every position.

@@ -156,10 +156,20 @@ inline int parse_model_file(const char* path, ModelFileView& mv, std::string& er
     mv.vocab.emplace_back(reinterpret_cast<const char*>(p), (size_t)len);
     p += len;
   }
-  // special-token fix-up (433-440).  The reference tests n_vocab == 51865 only (594-596);
-  // large-v3 (51866) is multilingual as well, so >= is used.
-  if (hp.n_vocab >= 51865)
-    for (int i = 0; i < 6; ++i) mv.special[i] += 1;
+  // special-token fix-up (433-440).  The reference tests n_vocab == 51865 only (594-596) and shifts
+  // eot, sot, prev, solm, not, beg by one.  A vocabulary with MORE language tokens (large-v3: 51866 = one
+  // extra language) moves every id behind the language block by the number of extra languages as well --
+  // upstream's `dt = num_languages - 98` rule: translate / transcribe and prev, solm, not, beg shift by
+  // `extra`; eot and sot sit in front of the language block and keep the single shift.  With 51865 entries
+  // this is exactly the reference's fix-up.
+  if (hp.n_vocab >= 51865) {
+    const int extra = hp.n_vocab - 51865;
+    mv.special[0] += 1;                                   // eot
+    mv.special[1] += 1;                                   // sot
+    for (int i = 2; i < 6; ++i) mv.special[i] += 1 + extra;   // prev, solm, not, beg
+    mv.special[6] += extra;                               // translate
+    mv.special[7] += extra;                               // transcribe
+  }
   // ids the file has no text for get the reference's placeholder names (442-467)
   for (int i = mv.n_vocab_file; i < hp.n_vocab; ++i) {
     const int eot = mv.special[0], sot = mv.special[1], prev = mv.special[2], tnot = mv.special[4], beg = mv.special[5];
