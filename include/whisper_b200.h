@@ -171,6 +171,10 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
                      uint16_t* out_f16 /* [n_seg*T][H*64] */);
 int wb_dbg_layernorm(wb_ctx* ctx, int rows, int d, const float* x, const float* w, const float* b,
                      uint16_t* out_f16);
+/* With wb_config.reserved[1] = 1 (or WB_CANARY=1 in the environment) every device buffer of the handle is allocated
+ * between two 256-byte guard zones; this returns how many guard zones have been written into since (0 = no kernel
+ * wrote outside its buffers; -1 = the handle has no guards). */
+int wb_dbg_canary_check(wb_ctx* ctx);
 /* device-side timing of the last call of each kind, in microseconds, per kernel family */
 int wb_kernel_time_us(const wb_ctx* ctx, const char* family, double* total_us, int64_t* launches);
 

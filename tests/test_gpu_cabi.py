@@ -27,7 +27,7 @@ def test_main_replay_in_c_vs_oracle(pkg, pyoracle, model_path, tmp_path, arch):
     orc = pyoracle.Oracle(model_path(arch))
     ref_mel = orc.pcm_to_mel(pcm)
     ref_enc = orc.encode(0)
-    ref_logits = orc.decode([orc.token_sot], 0)
+    ref_logits = orc.decode([orc.token_sot if orc.token_sot < orc.n_vocab else 7], 0)   # main_replay.c's prompt rule
     mel = np.fromfile(prefix + ".mel.f32", dtype=np.float32).reshape(ref_mel.shape)
     enc = np.fromfile(prefix + ".enc.f32", dtype=np.float32).reshape(ref_enc.shape)
     logits = np.fromfile(prefix + ".logits.f32", dtype=np.float32)

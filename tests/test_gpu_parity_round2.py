@@ -301,3 +301,34 @@ def test_norm_scope_segment(pkg, pyoracle, model_path):
         api.whisper_encode(ctx, 1, [0, fpw], clip_ids=[0, 0])
         assert rel_l2(ctx.encoder_out(1), ref) < ENC_TOL, (scope, rel_l2(ctx.encoder_out(1), ref))
         ctx.close()
+
+
+@pytest.mark.parametrize("arch", ["micro", "tiny"])
+def test_no_kernel_writes_outside_its_buffers(pkg, model_path, arch):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_compute_sanitizer.txt), so the library carries its own
+    check: with canary=True every device buffer sits between two 256-byte guard zones, and after the whole hot path
+    -- mel, encode at two audio contexts with ragged batches, prompt pass, greedy steps -- every guard zone must still
+    hold its fill pattern."""
+    from whisper_rs_b200 import api
+    hp = pkg.ggml_file.ARCHS[arch]
+    n = 2 * hp.n_audio_ctx * 160
+    S = 3
+    ctx = api.WhisperContext.new(model_path(arch), max_segments=S, max_clips=S, max_clip_samples=n, canary=True, checkpoints=True)
+    assert ctx.canary_check() == 0
+    clips = np.stack([pkg.synth.make_segment(120 + s, n, 0.1) for s in range(S)])
+    eot = hp.n_vocab - 1
+    for n_ctx, n_seg in ((0, S), (hp.n_audio_ctx // 3, 2), (0, 1), (hp.n_audio_ctx - 1, S)):
+        ctx.set_audio_ctx(n_ctx)
+        api.whisper_pcm_to_mel(ctx, clips)
+        api.whisper_encode(ctx, 1, [0] * n_seg, clip_ids=list(range(n_seg)))
+        ctx.encoder_digest(n_seg)
+        api.whisper_decode(ctx, np.tile(np.arange(1, 6, dtype=np.int32), (n_seg, 1)), 0)
+        api.whisper_decode_greedy(ctx, [7], 9, n_seqs=n_seg, eot=eot)
+        assert ctx.canary_check() == 0, (n_ctx, n_seg)
+    api.whisper_pcm_to_mel(ctx, (clips[:2, : n // 2 + 77] * 32767).astype(np.int16))    # i16 ingest, ragged length
+    ctx.mel(1)
+    assert ctx.canary_check() == 0
+    ctx.close()
+    plain = api.WhisperContext.new(model_path(arch), max_segments=1, decode_capacity=False)
+    assert plain.canary_check() == -1                     # no guards unless asked for
+    plain.close()

@@ -55,7 +55,7 @@ class WhisperContext:
     def __init__(self, fname: str, max_segments: int = 1, max_clips: int = 1,
                  max_clip_samples: int = 480000, device: int = 0, checkpoints: bool = False,
                  stream: Optional[int] = None, decode_capacity: bool = True, time_kernels: bool = False,
-                 norm_scope: int = cabi.NORM_CLIP):
+                 norm_scope: int = cabi.NORM_CLIP, canary: bool = False):
         L = cabi.lib()
         cfg = cabi.WbConfig()
         L.wb_config_default(C.byref(cfg))
@@ -68,6 +68,7 @@ class WhisperContext:
         cfg.stream = stream
         cfg.decode_capacity = int(decode_capacity)
         cfg.reserved[0] = int(time_kernels)
+        cfg.reserved[1] = int(canary)
         self._h = C.c_void_p()
         _check(L.wb_ctx_create(fname.encode(), C.byref(cfg), C.byref(self._h)))
         hp = (C.c_int32 * 11)()
@@ -161,6 +162,10 @@ class WhisperContext:
         buf = C.create_string_buffer(n + 1)
         cabi.lib().wb_tokens_to_text(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, buf, n + 1)
         return buf.raw[:n]
+
+    def canary_check(self) -> int:
+        """Guard zones around the handle's device buffers that a kernel has written into (needs canary=True)."""
+        return int(cabi.lib().wb_dbg_canary_check(self._h))
 
     def timings(self) -> dict:
         t = cabi.WbTimings()

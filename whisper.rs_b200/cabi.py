@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
                               C.c_int, C.c_void_p]
     L.wb_dbg_attention.argtypes = [vp, C.c_int, C.c_int, C.c_int, u16p, u16p]
     L.wb_dbg_layernorm.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, u16p]
+    L.wb_dbg_canary_check.argtypes = [vp]
     L.wb_kernel_time_us.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L
     return L

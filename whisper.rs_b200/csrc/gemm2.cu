@@ -291,12 +291,21 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
       const long long ln_row = (long long)it.b * args.M_rows + ln_m;
       float2 ln_st = make_float2(0.0f, 0.0f);
       float ln_c = 0.0f;
-      if (LN == 2 && ln_m < args.M_rows) {   // partial sums in slot order
-        const float2* pp = args.ln_part_in + ln_row * args.ln_parts;
-        for (int p = 0; p < args.ln_parts; ++p) {
-          const float2 v = __ldcg(pp + p);   // written by the previous kernel: L2, not the read-only path
-          ln_st.x += v.x;
-          ln_st.y += v.y;
+      if (LN == 2 && ln_m < args.M_rows) {
+        // the row's partial sums, two slots per 16-byte load, every load in flight before the first is used (one L2
+        // round trip under the accumulator wait, as the bias), added in slot order
+        constexpr int MAXP2 = 5;   // ln_parts = 2 * (d / tile width) <= 10 for d <= 1280
+        const float4* pp = reinterpret_cast<const float4*>(args.ln_part_in + ln_row * args.ln_parts);
+        const int p2 = args.ln_parts >> 1;
+        float4 pv[MAXP2];
+#pragma unroll
+        for (int p = 0; p < MAXP2; ++p) pv[p] = p < p2 ? __ldcg(pp + p) : make_float4(0.f, 0.f, 0.f, 0.f);   // L2: written by the previous kernel
+#pragma unroll
+        for (int p = 0; p < MAXP2; ++p) {
+          ln_st.x += pv[p].x;
+          ln_st.y += pv[p].y;
+          ln_st.x += pv[p].z;
+          ln_st.y += pv[p].w;
         }
       }
       if (LN == 1 && ln_m < args.M_rows) ln_c = __ldcg(args.ln_center + ln_row);
@@ -633,7 +642,8 @@ cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st) {
   a.ln_parts = g.epi.ln_parts;
   a.ln_center = g.epi.ln_center;
   if (a.ln_part_out && a.ln_parts != 2 * a.n_tiles) return cudaErrorInvalidValue;   // one slot per (N tile, epilogue half)
-  if ((a.ln_part_out || a.ln_part_in) && (!a.ln_center || a.ln_parts < 1)) return cudaErrorInvalidValue;
+  if ((a.ln_part_out || a.ln_part_in) && (!a.ln_center || a.ln_parts < 2 || a.ln_parts > 10 || (a.ln_parts & 1)))
+    return cudaErrorInvalidValue;
   a.ln_inv_d = g.K > 0 ? 1.0f / (float)g.K : 0.0f;
   a.ln_eps = g.epi.ln_eps;
   a.dbg = g.dbg;

@@ -647,6 +647,10 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   memcpy(ctx->special, mv.special, sizeof(mv.special));
   ctx->vocab = mv.vocab;
   ctx->time_kernels = cfg.reserved[0] != 0;
+  {
+    const char* cv = getenv("WB_CANARY");
+    ctx->canary = cfg.reserved[1] != 0 || (cv && cv[0] == '1');
+  }
   auto bail = [&](int code) {
     std::string m = ctx->err;
     wb_ctx_free(ctx);
@@ -748,6 +752,7 @@ void wb_ctx_free(wb_ctx* ctx) {
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   ctx->free_events.clear();
   if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
+  if (ctx->enc_graph.exec) cudaGraphExecDestroy(ctx->enc_graph.exec);
   for (void* p : ctx->allocs) cudaFree(p);
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)
@@ -1112,11 +1117,13 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
     ctx->pad_T = T;
   }
   const bool fold = ctx->ln_fold;
+  const int norm_mode = ctx->mel_materialized ? 0 : ctx->cfg.norm_scope == WB_NORM_SEGMENT ? 2 : 1;
 
+  // every launch of one encode: run directly, or captured once per shape into a CUDA graph and replayed (below)
+  auto encode_launches = [&]() -> int {
   // E0: mel window -> token-major F16 rows with zero padding rows (1816-1829)
   // fused with clamp_and_normalize (1654-1671) when the stored mel still holds log10 values: with the clip's maximum
   // (WB_NORM_CLIP, the reference) or the window's own (WB_NORM_SEGMENT)
-  const int norm_mode = ctx->mel_materialized ? 0 : ctx->cfg.norm_scope == WB_NORM_SEGMENT ? 2 : 1;
   if (norm_mode == 2) {
     LaunchTimer t(ctx, "mel_window_max");
     WB_CK(launch_fill_i32(ctx->d_seg_max, n_seg, mel_enc_ordered_host(-1e20f), st));
@@ -1256,6 +1263,53 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
         if ((rc = probe_f16(5 + L + 2 * il, ctx->cross + (size_t)(2 * il + 1) * ctx->cross_slab, T, d, d, (long long)T * d))) return rc;
       }
     }
+  }
+  return WB_OK;
+  };
+
+  // The ~6 L + 6 launches of an encode depend only on (n_seg, T, the mel's frame count, the normalisation mode):
+  // captured once per such shape and replayed, so a call costs one graph launch of host time instead of one launch
+  // per kernel (the segment table is uploaded outside the graph: its pinned source slot changes from call to call).
+  // Not used with per-kernel timing or checkpoints (both add launches that depend on the mode).  WB_ENC_GRAPH=0: off.
+  static const bool graph_off = [] { const char* e = getenv("WB_ENC_GRAPH"); return e && e[0] == '0'; }();
+  if (!graph_off && !ctx->time_kernels && !chk) {
+    wb::EncodeGraph& eg = ctx->enc_graph;
+    const bool same = eg.n_seg == n_seg && eg.T == T && eg.mel_n_len == ctx->mel_n_len && eg.norm_mode == norm_mode;
+    if (!same) {
+      // first call of a shape: run directly (each kernel instantiation opts in to its shared-memory size at its first
+      // launch -- not something to do inside a capture); the next call of the same shape captures
+      if (eg.exec) {
+        cudaGraphExecDestroy(eg.exec);
+        eg.exec = nullptr;
+      }
+      eg.n_seg = n_seg;
+      eg.T = T;
+      eg.mel_n_len = ctx->mel_n_len;
+      eg.norm_mode = norm_mode;
+      if ((rc = encode_launches())) return rc;
+    } else {
+    if (!eg.exec) {
+      const int64_t l0 = ctx->tm.n_kernel_launches;
+      cudaGraph_t graph = nullptr;
+      WB_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = encode_launches();
+      const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+      eg.launches = (int)(ctx->tm.n_kernel_launches - l0);
+      ctx->tm.n_kernel_launches = l0;   // counted per replay below
+      if (rc != WB_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (e_end != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaStreamEndCapture (encode)", e_end);
+      const cudaError_t e_inst = cudaGraphInstantiate(&eg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e_inst != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaGraphInstantiate (encode)", e_inst);
+    }
+    WB_CK(cudaGraphLaunch(eg.exec, st));
+    ctx->tm.n_kernel_launches += eg.launches;
+    }
+  } else if ((rc = encode_launches())) {
+    return rc;
   }
   cudaEventRecord(ctx->ev[1][1], st);
   ctx->ev_used[1] = true;
@@ -1557,6 +1611,29 @@ int wb_dbg_attention(wb_ctx* ctx, int n_seg, int T, int H, const uint16_t* qkv_f
   DBG_CK(cudaMemcpy(out_f16, dO, M * d * 2, cudaMemcpyDeviceToHost));
   cleanup();
   return rc;
+}
+
+// guard zones around every device buffer (see dev_alloc): returns the number of guard zones that no longer hold
+// their fill pattern (0 = no kernel wrote outside its buffers), -1 if the context was created without guards
+int wb_dbg_canary_check(wb_ctx* ctx) {
+  if (!ctx) return WB_ERR_UNEXPECTED;
+  if (!ctx->canary) return -1;
+  cudaSetDevice(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return WB_ERR_TENSOR_OP;
+  std::vector<uint8_t> h(2 * WB_GUARD);
+  int bad = 0;
+  for (const auto& g : ctx->guarded) {
+    if (cudaMemcpy(h.data(), g.user - WB_GUARD, WB_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(h.data() + WB_GUARD, g.user + g.bytes, WB_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return WB_ERR_TENSOR_OP;
+    bool front_ok = true, back_ok = true;
+    for (size_t i = 0; i < WB_GUARD; ++i) {
+      front_ok = front_ok && h[i] == 0xA5;
+      back_ok = back_ok && h[WB_GUARD + i] == 0xA5;
+    }
+    bad += (front_ok ? 0 : 1) + (back_ok ? 0 : 1);
+  }
+  return bad;
 }
 
 int wb_dbg_layernorm(wb_ctx* ctx, int rows, int d, const float* x, const float* w, const float* b, uint16_t* out_f16) {

@@ -48,6 +48,12 @@ struct EncodeMaps {       // wb_encode's tensor maps for one (n_seg, audio conte
   AttnProblem ap;
 };
 
+struct EncodeGraph {      // the launches of one wb_encode, captured for one shape
+  cudaGraphExec_t exec = nullptr;
+  int n_seg = 0, T = 0, mel_n_len = 0, norm_mode = -1;
+  int launches = 0;       // kernels one replay runs (n_kernel_launches accounting)
+};
+
 struct PendingEvent {   // one bracketed launch whose events have not been read yet
   const char* fam;
   cudaEvent_t a, b;
@@ -73,6 +79,9 @@ struct wb_ctx {
   int32_t special[8]{};
   std::vector<std::string> vocab;   // id_to_token (src/main.rs:544)
   std::vector<void*> allocs;
+  bool canary = false;                // guard zones around every device buffer (wb_dbg_canary_check)
+  struct Guarded { uint8_t* user; size_t bytes; };
+  std::vector<Guarded> guarded;
 
   // ---- weights
   const float* e_pe = nullptr;
@@ -135,6 +144,7 @@ struct wb_ctx {
   size_t cross_slab = 0;              // elements per slab = max_segments * T * d
   int Tp = 0;
   wb::EncodeMaps enc_maps;
+  wb::EncodeGraph enc_graph;
   int enc_n_seg = 0;                  // segments of the last wb_encode
   int exp_n_audio_ctx = 0;            // exp_n_audio_ctx (src/main.rs:362): > 0 shortens the encoder's audio context
   int enc_T = 0;                      // audio context the last wb_encode ran with (rows per segment of its outputs)

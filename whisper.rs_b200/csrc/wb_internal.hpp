@@ -17,18 +17,30 @@ void set_global_error(const std::string& msg);
     if (e_ != cudaSuccess) return wb::fail(ctx, WB_ERR_TENSOR_OP, #expr, e_); \
   } while (0)
 
+// With wb_config.reserved[1] != 0 (or WB_CANARY=1) every device buffer sits between two WB_GUARD-byte guard zones
+// filled with 0xA5; wb_dbg_canary_check counts the guard zones a kernel has written into (compute-sanitizer is not
+// available on every pool: this catches out-of-bounds WRITES next to any buffer on the real hardware at full speed).
+constexpr size_t WB_GUARD = 256;
 template <class T>
 int dev_alloc(wb_ctx* ctx, T** out, size_t count, bool zero = true) {
   void* p = nullptr;
   const size_t bytes = (count ? count : 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&p, bytes);
+  const size_t guard = ctx->canary ? WB_GUARD : 0;
+  cudaError_t e = cudaMalloc(&p, bytes + 2 * guard);
   if (e != cudaSuccess) return fail(ctx, WB_ERR_NOT_ENOUGH_SPACE, "cudaMalloc", e);
+  ctx->allocs.push_back(p);
+  uint8_t* user = reinterpret_cast<uint8_t*>(p) + guard;
+  if (guard) {
+    e = cudaMemsetAsync(p, 0xA5, guard, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(user + bytes, 0xA5, guard, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaMemset", e);
+    ctx->guarded.push_back({user, bytes});
+  }
   if (zero) {
-    e = cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    e = cudaMemsetAsync(user, 0, bytes, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "cudaMemset", e);
   }
-  ctx->allocs.push_back(p);
-  *out = reinterpret_cast<T*>(p);
+  *out = reinterpret_cast<T*>(user);
   return WB_OK;
 }
 
