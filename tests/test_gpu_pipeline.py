@@ -139,3 +139,35 @@ def test_assemble_segments(pkg, model_path):
     assert t[1].tid == beg and t[4].tid == beg + 50
     assert all(x.t0 >= segs[1].t0 for x in segs[1].tokens) and len(segs[1].tokens) == 8
     ctx.close()
+
+
+def test_long_form_prompt_past_vs_oracle(pkg, pyoracle, model_path):
+    """prompt_past (src/main.rs:356): windows decoded in order, each conditioned on the text decoded before it
+    ([prev] + the last n_text_ctx / 2 tokens + [sot]).  The oracle replays the same prompts window by window."""
+    from whisper_rs_b200 import api, pipeline
+    arch = "micro"
+    hp = pkg.ggml_file.ARCHS[arch]
+    fpw = 2 * hp.n_audio_ctx
+    n = 4 * fpw * 160
+    pcm = pkg.synth.make_segment(310, n, silent_tail_s=0.0)
+    eot = hp.n_vocab - 1
+    ctx = api.WhisperContext.new(model_path(arch), max_segments=1, max_clips=1, max_clip_samples=n)
+    ctx.token_prev = 3                                    # micro's vocabulary is smaller than the real special ids
+    init = [7]
+    toks, prompts = pipeline.transcribe_long_form(ctx, pcm, prompt_init=init, max_new=6, eot=eot)
+    assert len(toks) == 4 and prompts[0] == init
+    assert prompts[1][0] == 3 and prompts[1][-1] == 7 and prompts[1][1:-1] == [int(x) for x in toks[0] if x != eot]
+    assert len(prompts[3]) <= 1 + hp.n_text_ctx // 2 + len(init)
+    assert prompts[3][1:-1][-len(toks[2]):] == [int(x) for x in toks[2] if x != eot][-len(toks[2]):]
+    orc = pyoracle.Oracle(model_path(arch))
+    orc.pcm_to_mel(pcm)
+    agree = 0
+    for w in range(4):
+        orc.encode(w * fpw)
+        rt, rm = orc.decode_greedy(prompts[w], 6, eot=eot)        # same prompt: the conditioning is what is under test
+        agree += _check_greedy(toks[w], len(toks[w]), rt, rm)
+    assert agree >= 8
+    # unconditioned decoding of the same clip differs from window 1 on (the prompt matters)
+    toks_u, prompts_u = pipeline.transcribe_long_form(ctx, pcm, prompt_init=init, max_new=6, eot=eot, condition_on_previous=False)
+    assert all(p == init for p in prompts_u)
+    ctx.close()

@@ -59,12 +59,13 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
 // ---------------------------------------------------------------------------------------------
 // D1: x[s][i][:] = d_te[tok[s][i]][:] + d_pe[n_past + i][:]
 // With `stats` (the LayerNorm-folded single-token step): also leaves the row's (sum, sum of squares) in
-// stats[row] -- the statistics of layer 0's attn_ln -- and an F16 copy of the row, and block 0 clears the
-// other `n_clear` statistics slots of the step (their producers accumulate with atomics).
+// stats[row] -- the statistics of layer 0's attn_ln -- and an F16 copy of the row, and block 0 clears this
+// launch's rows of the other `n_clear_slots` statistics slots of the step (their producers accumulate with
+// atomics; another sequence group's rows of the same slots may be in use on another stream).
 __global__ void __launch_bounds__(128)
 embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
              int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, float2* __restrict__ stats,
-             __half* __restrict__ x16, int n_clear) {
+             __half* __restrict__ x16, int n_clear_slots) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ float red[2][4];
@@ -94,8 +95,11 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
     __syncthreads();
     if (threadIdx.x == 0)
       stats[row] = make_float2((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]), (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
-    if (blockIdx.x == 0)
-      for (int c = threadIdx.x; c < n_clear; c += blockDim.x) stats[DEC_LN_ROWS + c] = make_float2(0.0f, 0.0f);
+    if (blockIdx.x == 0) {
+      const int rows = gridDim.x;
+      for (int c = threadIdx.x; c < n_clear_slots * rows; c += blockDim.x)
+        stats[(size_t)(1 + c / rows) * DEC_LN_ROWS + c % rows] = make_float2(0.0f, 0.0f);
+    }
   }
 }
 
@@ -759,10 +763,10 @@ __global__ void advance_kernel(int* n_past, int add, int* step) {
 
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
                          const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats, __half* x16,
-                         int n_clear) {
+                         int n_clear_slots) {
   if (stats && n_seq * n_tok > DEC_LN_ROWS) return cudaErrorInvalidValue;
   return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x, stats,
-                    x16, n_clear);
+                    x16, n_clear_slots);
 }
 
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,

@@ -34,12 +34,18 @@ constexpr int SKEW = 16;
 __device__ __forceinline__ int pcm_pos(int j) { return j + SKEW * (j / HOP); }
 constexpr int SPAN_SKEWED = SPAN + SKEW * ((SPAN + HOP - 1) / HOP);
 
+// shared-memory strides chosen against bank conflicts (ncu, round 2: a third of the kernel's shared-memory wavefronts
+// were conflict replays): pass B's lanes read Y'[q][.] for consecutive q -- 9 float2 per k2 (18 words) puts the 13 values of
+// q on 13 different even banks (8 float2 = 16 words put them on two); a frame stride of 232 float2 (= 16 mod 32 words)
+// keeps pass A's two frames per half-warp on disjoint banks; pass C's 16 lanes read the same bin of 16 frames -- 205
+// words per frame (13 mod 32, odd) spreads them over 16 banks (204 = 12 mod 32 gave 8).
+constexpr int A_K2 = 9, A_FRAME = 232, PW_STRIDE = NBIN + 4;
 struct MelSmem {
   union {                    // the samples are dead once pass A has windowed them: the power spectrum reuses their space
     float pcm[SPAN_SKEWED];
-    float pw[F][NBIN + 3];
+    float pw[F][PW_STRIDE];
   };
-  float2 a[F][200];          // pass A output: Y'[k2][n1] at [k2 * 8 + n1]
+  float2 a[F][A_FRAME];      // pass A output: Y'[k2][n1] at [k2 * A_K2 + n1]
   MelTableBlob tab;          // twiddles, window, filterbank taps (wb_kernels.hpp)
 };
 constexpr int TAB4 = (int)(sizeof(MelTableBlob) / 16);
@@ -208,7 +214,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
       for (int e = 0; e < 5; ++e) {
         const int k2 = c + 5 * e;
         const float2 y = (k2 == 0) ? x[e] : cmul(x[e], s.tab.w200[n1 * k2]);   // n1 k2 <= 7 * 24
-        s.a[f][k2 * 8 + n1] = y;
+        s.a[f][k2 * A_K2 + n1] = y;
       }
     }
   }
@@ -218,7 +224,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
     const int f = it / 13, q = it - f * 13;
     float2 xa[8], za[8];
 #pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) xa[n1] = s.a[f][q * 8 + n1];
+    for (int n1 = 0; n1 < 8; ++n1) xa[n1] = s.a[f][q * A_K2 + n1];
     dft8(xa, za);                                           // za[k1] = Z[q + 25 k1]
     float* pw = s.pw[f];
     if (q == 0) {
@@ -230,7 +236,7 @@ mel_frames_kernel(const MelTables tb, const void* __restrict__ pcm_v, size_t n_s
     } else {
       float2 xb[8], zb[8];
 #pragma unroll
-      for (int n1 = 0; n1 < 8; ++n1) xb[n1] = s.a[f][(25 - q) * 8 + n1];
+      for (int n1 = 0; n1 < 8; ++n1) xb[n1] = s.a[f][(25 - q) * A_K2 + n1];
       dft8(xb, zb);                                         // zb[k1] = Z[(25 - q) + 25 k1]
 #pragma unroll
       for (int k1 = 0; k1 < 8; ++k1) {

@@ -753,6 +753,11 @@ void wb_ctx_free(wb_ctx* ctx) {
   ctx->free_events.clear();
   if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
   if (ctx->enc_graph.exec) cudaGraphExecDestroy(ctx->enc_graph.exec);
+  for (int g = 0; g < WB_MAX_DEC_GROUPS; ++g) {
+    if (ctx->dec_group_stream[g]) cudaStreamDestroy(ctx->dec_group_stream[g]);
+    if (ctx->dec_group_done[g]) cudaEventDestroy(ctx->dec_group_done[g]);
+  }
+  if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
   for (void* p : ctx->allocs) cudaFree(p);
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)

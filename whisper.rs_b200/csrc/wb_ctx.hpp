@@ -67,6 +67,7 @@ struct KernelClock {   // device time per kernel family (CUDA events on the hand
 }  // namespace wb
 
 constexpr int WB_N_TICKETS = 8;
+constexpr int WB_MAX_DEC_GROUPS = 4;
 
 struct wb_ctx {
   wb_config cfg{};
@@ -174,6 +175,10 @@ struct wb_ctx {
   cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
   int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;
   int step_graph_enc_T = 0, step_graph_n_split = 0;   // host parameters decode_pass bakes into the captured launches
+  int step_graph_groups = 0;                     // sequence groups (parallel branches) of the captured step
+  cudaStream_t dec_group_stream[WB_MAX_DEC_GROUPS] = {};   // capture-only streams of the branches
+  cudaEvent_t dec_group_done[WB_MAX_DEC_GROUPS] = {};
+  cudaEvent_t dec_fork = nullptr;
 
   // ---- results read back without blocking (wb_encoder_digest_async / wb_wait)
   cudaEvent_t ev_ticket[WB_N_TICKETS] = {};

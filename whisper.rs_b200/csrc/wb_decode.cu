@@ -35,7 +35,7 @@ static int make_act_maps(wb_ctx* ctx, ActMaps& am, const __half* base, int K, in
 // few rows (one token per sequence, <= 32 sequences): the HBM-bound skinny kernel, every 16 weight
 // rows on their own CTA (decode_kernels.cu); more rows: the tcgen05 GEMM in swap-AB form
 static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const ActMaps& act, int R, GemmEpilogue epi,
-                           const char* family, float* top2 = nullptr);
+                           const char* family, float* top2 = nullptr, cudaStream_t st = nullptr);
 
 static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, int R, GemmEpilogue epi,
                             const char* family) {
@@ -58,8 +58,10 @@ static int run_gemm_swapped(wb_ctx* ctx, const Linear& l, const ActMaps& act, in
 }
 
 static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const ActMaps& act, int R, GemmEpilogue epi,
-                           const char* family, float* top2) {
+                           const char* family, float* top2, cudaStream_t st) {
+  if (!st) st = ctx->stream;
   if (R > 32 || l.K % 64 != 0) {
+    if (st != ctx->stream) return fail_msg(ctx, WB_ERR_TENSOR_OP, "galois tensor:'sequence groups need the skinny linear kernel'");
     if (epi.ln_stats_in || epi.ln_stats_out) return fail_msg(ctx, WB_ERR_TENSOR_OP, "galois tensor:'folded LayerNorm needs the skinny linear kernel'");
     return run_gemm_swapped(ctx, l, act, R, epi, family);
   }
@@ -92,7 +94,7 @@ static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const 
     a.x16_ld = epi.x16_ld;
   }
   LaunchTimer t(ctx, family);
-  WB_CK(launch_decode_linear(a, ctx->stream));
+  WB_CK(launch_decode_linear(a, st));
   return WB_OK;
 }
 
@@ -190,7 +192,13 @@ static bool dec_skip(const char* what) {
   return e && strstr(e, what) != nullptr;
 }
 
-static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok) {
+// `seq0` / `st`: the pass covers sequences [seq0, seq0 + n_seq) and is issued on stream `st` -- the single-token step
+// of a large batch is split into sequence groups that run on parallel branches of the step graph (wb_decode_greedy):
+// a group's chain of ~100 small latency-bound kernels overlaps the other groups' HBM-bound cross-attention.  Every
+// activation buffer is row-indexed, so a group simply works on its rows (seq0 > 0 needs n_tok == 1).
+static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok, int seq0 = 0, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
+  if (seq0 > 0 && n_tok != 1) return fail_msg(ctx, WB_ERR_UNEXPECTED, "Unexpected: sequence groups are single-token passes");
   const ModelHParams& hp = ctx->hp;
   const bool skip_cross = dec_skip("cross"), skip_self = dec_skip("self"), skip_lin = dec_skip("linear"),
              skip_logits = dec_skip("logits");
@@ -199,145 +207,160 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok)
   const int n_ctx = hp.n_text_ctx;
   const int R = n_seq * n_tok;
   const long long ld_kv = d;   // cross K / V of one layer: dense [seg][T][d]
-  cudaStream_t st = ctx->stream;
   int rc;
+  // this group's rows of every buffer
+  const size_t r0 = (size_t)seq0 * n_tok;
+  tokens_dev += r0;
+  float* const dx = ctx->dx + r0 * d;
+  __half* const d_ln = ctx->d_ln + r0 * d;
+  __half* const d_qkv = ctx->d_qkv + r0 * 3 * d;
+  __half* const d_att = ctx->d_att + r0 * d;
+  __half* const d_q = ctx->d_q + r0 * d;
+  __half* const d_hid = ctx->d_hid + r0 * 4 * d;
+  __half* const d_lnf = ctx->d_lnf + (size_t)seq0 * d;
+  float* const d_logits = ctx->d_logits + (size_t)seq0 * hp.n_vocab;
+  float* const d_top2 = ctx->d_top2 + (size_t)seq0 * decode_linear_parts(hp.n_vocab) * 3;
   // few rows (the single-token step): LayerNorm folded into the linears around it -- the producers of the
   // residual stream leave row statistics + an F16 copy (d_ln), the consumers apply them (slot 3 il + {0, 1, 2} =
   // attn_ln, cross_attn_ln, mlp_ln of layer il).  Many rows (prompt pass on the tcgen05 GEMM): a LayerNorm
   // kernel without affine part in front of the same folded weights.
   const bool fold = R <= DEC_LN_ROWS && d % 64 == 0;
-  auto slot = [&](int i) { return ctx->dec_ln_stats + (size_t)i * DEC_LN_ROWS; };
+  auto slot = [&](int i) { return ctx->dec_ln_stats + (size_t)i * DEC_LN_ROWS + r0; };
   {
     LaunchTimer t(ctx, "dec_embed");
-    WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, ctx->dx, st,
-                       fold ? ctx->dec_ln_stats : nullptr, ctx->d_ln, fold ? DEC_LN_ROWS * (3 * Lt) : 0));
+    WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, dx, st,
+                       fold ? slot(0) : nullptr, d_ln, fold ? 3 * Lt : 0));
   }
   const int n_split = n_tok <= 8 ? decode_cross_splits(n_seq, H, T, ctx->num_sms) : 1;
   for (int il = 0; il < Lt; ++il) {
     const DecLayer& l = ctx->dec[il];
     if (!fold) {   // D2: self-attention
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(dx, ctx->d_ones, ctx->d_zeros, R, d, d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
-      e.out = ctx->d_qkv;
+      e.out = d_qkv;
       e.out_f16 = 1;
       e.out_ld = 3 * d;
       if (fold) e.ln_stats_in = slot(3 * il);
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.qkv, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.qkv, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!skip_self) {
       LaunchTimer t(ctx, "dec_self_attn");
-      __half* kc = ctx->self_k + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
-      __half* vc = ctx->self_v + (size_t)il * ctx->cfg.max_segments * n_ctx * d;
-      WB_CK(launch_decode_self_attn(ctx->d_qkv, d, kc, vc, n_seq, n_tok, ctx->d_npast, n_ctx, H, ctx->d_att, st));
+      __half* kc = ctx->self_k + ((size_t)il * ctx->cfg.max_segments + seq0) * n_ctx * d;
+      __half* vc = ctx->self_v + ((size_t)il * ctx->cfg.max_segments + seq0) * n_ctx * d;
+      WB_CK(launch_decode_self_attn(d_qkv, d, kc, vc, n_seq, n_tok, ctx->d_npast, n_ctx, H, d_att, st));
     }
     {
       GemmEpilogue e;
-      e.residual = ctx->dx;
+      e.residual = dx;
       e.res_ld = d;
-      e.out = ctx->dx;
+      e.out = dx;
       e.out_f16 = 0;
       e.out_ld = d;
       if (fold) {
         e.ln_stats_out = slot(3 * il + 1);
-        e.x16_out = ctx->d_ln;
+        e.x16_out = d_ln;
         e.x16_ld = d;
       }
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.out, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.out, d_att, ctx->m_att, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!fold) {   // D3: cross-attention over memory_cross_k/v written by wb_encode
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(dx, ctx->d_ones, ctx->d_zeros, R, d, d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
-      e.out = ctx->d_q;
+      e.out = d_q;
       e.out_f16 = 1;
       e.out_ld = d;
       if (fold) e.ln_stats_in = slot(3 * il + 1);
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.cq, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.cq, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!skip_cross) {
       LaunchTimer t(ctx, "dec_cross_attn");
-      const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab;
+      const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab + (size_t)seq0 * T * d;   // segment seq0 onwards
       // (timing experiment WB_DEC_SKIP=headmajor: read the slab as if it were head-major -- garbage results)
       const bool hm = dec_skip("headmajor");
-      WB_CK(launch_decode_cross_attn(ctx->d_q, d, kx, kx + ctx->cross_slab, hm ? 64 : ld_kv,
-                                     hm ? (long long)ctx->cfg.max_segments * T * 64 : 64, n_seq, n_tok, T, H, ctx->d_att,
-                                     ctx->d_part_o, ctx->d_part_ml, n_split, ctx->d_split_cnt, st));
+      WB_CK(launch_decode_cross_attn(d_q, d, kx, kx + ctx->cross_slab, hm ? 64 : ld_kv,
+                                     hm ? (long long)ctx->cfg.max_segments * T * 64 : 64, n_seq, n_tok, T, H, d_att,
+                                     ctx->d_part_o + (size_t)seq0 * H * 8 * 64, ctx->d_part_ml + (size_t)seq0 * H * 8 * 2, n_split,
+                                     ctx->d_split_cnt + (size_t)seq0 * H, st));
     }
     {
       GemmEpilogue e;
-      e.residual = ctx->dx;
+      e.residual = dx;
       e.res_ld = d;
-      e.out = ctx->dx;
+      e.out = dx;
       e.out_f16 = 0;
       e.out_ld = d;
       if (fold) {
         e.ln_stats_out = slot(3 * il + 2);
-        e.x16_out = ctx->d_ln;
+        e.x16_out = d_ln;
         e.x16_ld = d;
       }
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.cout, ctx->d_att, ctx->m_att, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.cout, d_att, ctx->m_att, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!fold) {   // D4: MLP
       LaunchTimer t(ctx, "dec_layernorm");
-      WB_CK(launch_layernorm(ctx->dx, ctx->d_ones, ctx->d_zeros, R, d, ctx->d_ln, nullptr, st, 0, true));
+      WB_CK(launch_layernorm(dx, ctx->d_ones, ctx->d_zeros, R, d, d_ln, nullptr, st, 0, true));
     }
     {
       GemmEpilogue e;
       e.gelu = 1;
-      e.out = ctx->d_hid;
+      e.out = d_hid;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
       if (fold) e.ln_stats_in = slot(3 * il + 2);
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc1, ctx->d_ln, ctx->m_ln, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc1, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     {
       GemmEpilogue e;
-      e.residual = ctx->dx;
+      e.residual = dx;
       e.res_ld = d;
-      e.out = ctx->dx;
+      e.out = dx;
       e.out_f16 = 0;
       e.out_ld = d;
       if (fold && il + 1 < Lt) {   // (decoder.ln in front of the logits keeps its kernel: d_te is shared with the embedding)
         e.ln_stats_out = slot(3 * il + 3);
-        e.x16_out = ctx->d_ln;
+        e.x16_out = d_ln;
         e.x16_ld = d;
       }
-      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc2, ctx->d_hid, ctx->m_hid, R, e, "dec_gemm"))) return rc;
+      if (!skip_lin && (rc = run_linear_rows(ctx, l.fc2, d_hid, ctx->m_hid, R, e, "dec_gemm", nullptr, st))) return rc;
     }
   }
   {   // D5: logits of the last position of every sequence
     LaunchTimer t(ctx, "dec_layernorm");
-    WB_CK(launch_layernorm(ctx->dx + (size_t)(n_tok - 1) * d, ctx->d_ln_w, ctx->d_ln_b, n_seq, d, ctx->d_lnf, nullptr,
+    WB_CK(launch_layernorm(dx + (size_t)(n_tok - 1) * d, ctx->d_ln_w, ctx->d_ln_b, n_seq, d, d_lnf, nullptr,
                            st, (long long)n_tok * d, true));
   }
   {
     GemmEpilogue e;
-    e.out = ctx->d_logits;
+    e.out = d_logits;
     e.out_f16 = 0;
     e.out_ld = hp.n_vocab;
     // <= 32 sequences: the skinny kernel also leaves per-CTA top-2 partials, so D6 never re-reads the logits
     ctx->logits_top2_valid = n_seq <= 32 && ctx->logits_lin.K % 64 == 0;
-    if (!skip_logits && (rc = run_linear_rows(ctx, ctx->logits_lin, ctx->d_lnf, ctx->m_lnf, n_seq, e, "dec_gemm_logits",
-                                              ctx->logits_top2_valid ? ctx->d_top2 : nullptr)))
+    if (!skip_logits && (rc = run_linear_rows(ctx, ctx->logits_lin, d_lnf, ctx->m_lnf, n_seq, e, "dec_gemm_logits",
+                                              ctx->logits_top2_valid ? d_top2 : nullptr, st)))
       return rc;
   }
   return WB_OK;
 }
 
 // D6 bookkeeping after a decode pass: from the top-2 partials when the skinny logits kernel ran
-static cudaError_t run_argmax(wb_ctx* ctx, int n_seqs, int max_new, int eot) {
+static cudaError_t run_argmax(wb_ctx* ctx, int n_seqs, int max_new, int eot, int seq0 = 0, cudaStream_t st = nullptr) {
   const ModelHParams& hp = ctx->hp;
+  if (!st) st = ctx->stream;
+  const size_t o = (size_t)seq0, om = (size_t)seq0 * max_new;   // this group's sequences
   if (ctx->logits_top2_valid)
-    return launch_argmax_partials(ctx->d_top2, decode_linear_parts(hp.n_vocab), n_seqs, ctx->d_next, ctx->d_margin,
-                                  ctx->d_out_tokens, ctx->d_out_margin, ctx->d_out_len, ctx->d_done, max_new, ctx->d_step,
-                                  eot, ctx->stream);
-  return launch_argmax(ctx->d_logits, n_seqs, hp.n_vocab, ctx->d_next, ctx->d_margin, ctx->d_out_tokens, ctx->d_out_margin,
-                       ctx->d_out_len, ctx->d_done, max_new, ctx->d_step, eot, ctx->stream);
+    return launch_argmax_partials(ctx->d_top2 + o * decode_linear_parts(hp.n_vocab) * 3, decode_linear_parts(hp.n_vocab), n_seqs,
+                                  ctx->d_next + o, ctx->d_margin + o, ctx->d_out_tokens + om, ctx->d_out_margin + om,
+                                  ctx->d_out_len + o, ctx->d_done + o, max_new, ctx->d_step, eot, st);
+  return launch_argmax(ctx->d_logits + o * hp.n_vocab, n_seqs, hp.n_vocab, ctx->d_next + o, ctx->d_margin + o,
+                       ctx->d_out_tokens + om, ctx->d_out_margin + om, ctx->d_out_len + o, ctx->d_done + o, max_new, ctx->d_step,
+                       eot, st);
 }
 
 static int check_decode_args(wb_ctx* ctx, int n_tok, int n_past, int n_seq) {
@@ -432,22 +455,65 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   // everything decode_pass bakes into its launches is part of the key: the audio context of the last encode (the
   // segment stride of the cross K/V and the key-range split of the cross-attention) as well as the batch shape
   const int enc_T = ctx->enc_T > 0 ? ctx->enc_T : hp.n_audio_ctx;
-  const int n_split = decode_cross_splits(n_seqs, hp.n_text_head, enc_T, ctx->num_sms);
+  // sequence groups: the step of a large batch runs as G parallel branches of the graph, each over its own block of
+  // sequences (multiples of 8 = the skinny linear's row groups).  A branch is a chain of ~8 L small kernels that is
+  // bound by launch / L2 latency except for its cross-attention, which streams 2 T d bytes per sequence and layer
+  // from HBM: with several branches in flight one group's latency-bound kernels run under another group's stream.
+  // The weights are read once per group (from L2 for all but the first).  Off by default (see the measurements below);
+  // WB_DEC_GROUPS=2|4 selects it.
+  int n_groups = 1;
+  {
+    static const int forced = [] { const char* e = getenv("WB_DEC_GROUPS"); return e ? atoi(e) : 0; }();
+    const double w_bytes = (14.0 * hp.n_text_layer * hp.n_text_state * hp.n_text_state + (double)hp.n_vocab * hp.n_text_state) * 2.0;
+    const double kv_bytes = (double)n_seqs * hp.n_text_layer * 2.0 * enc_T * hp.n_text_state * 2.0;
+    (void)w_bytes;
+    (void)kv_bytes;
+    // measured on B200 (tools/dec_groups.py, profiles/r02_dec_groups.jsonl): small B = 32: 1 group 0.755 ms/step, 2 groups
+    // 0.760, 4 groups 0.903; medium B = 32: 2.01 / 2.00 / 2.44; large-v3 B = 15: 2.10 / 2.48 -- the branches do not
+    // overlap usefully (a cross-attention grid fills every SM's registers while it runs), so the default stays 1
+    if (forced > 0) n_groups = forced;
+    if (n_seqs > 32) n_groups = 1;   // more than 32 rows: the tcgen05 swap-AB path, one stream
+    while (n_groups > 1 && (n_seqs + n_groups - 1) / n_groups < 8) n_groups >>= 1;
+    if (n_groups > WB_MAX_DEC_GROUPS) n_groups = WB_MAX_DEC_GROUPS;
+  }
+  const int per_group = n_groups > 1 ? (((n_seqs + n_groups - 1) / n_groups) + 7) / 8 * 8 : n_seqs;
+  const int n_split = decode_cross_splits(n_groups > 1 ? per_group : n_seqs, hp.n_text_head, enc_T, ctx->num_sms);
   if (use_graph && (ctx->step_graph == nullptr || ctx->step_graph_n_seq != n_seqs ||
                     ctx->step_graph_max_new != max_new || ctx->step_graph_eot != eot ||
-                    ctx->step_graph_enc_T != enc_T || ctx->step_graph_n_split != n_split)) {
+                    ctx->step_graph_enc_T != enc_T || ctx->step_graph_n_split != n_split ||
+                    ctx->step_graph_groups != n_groups)) {
     if (ctx->step_graph) {
       cudaGraphExecDestroy(ctx->step_graph);
       ctx->step_graph = nullptr;
     }
     cudaGraph_t graph = nullptr;
-    WB_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
-    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-    if (rc == WB_OK) {
-      e1 = run_argmax(ctx, n_seqs, max_new, eot);
-      e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
+    if (n_groups > 1 && !ctx->dec_group_stream[0]) {
+      for (int g = 0; g < WB_MAX_DEC_GROUPS; ++g) {
+        WB_CK(cudaStreamCreateWithFlags(&ctx->dec_group_stream[g], cudaStreamNonBlocking));
+        WB_CK(cudaEventCreateWithFlags(&ctx->dec_group_done[g], cudaEventDisableTiming));
+      }
+      WB_CK(cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming));
     }
+    WB_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (n_groups <= 1) {
+      rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
+      if (rc == WB_OK) e1 = run_argmax(ctx, n_seqs, max_new, eot);
+    } else {
+      // fork: every branch starts behind the previous step's bookkeeping on `st`; join: `st` waits for every branch
+      e1 = cudaEventRecord(ctx->dec_fork, st);
+      rc = WB_OK;
+      for (int g = 0, s0 = 0; s0 < n_seqs && rc == WB_OK && e1 == cudaSuccess; ++g, s0 += per_group) {
+        const int ng = n_seqs - s0 < per_group ? n_seqs - s0 : per_group;
+        cudaStream_t gs = ctx->dec_group_stream[g];
+        e1 = cudaStreamWaitEvent(gs, ctx->dec_fork, 0);
+        if (e1 == cudaSuccess) rc = decode_pass(ctx, ctx->d_next, ng, 1, s0, gs);
+        if (rc == WB_OK && e1 == cudaSuccess) e1 = run_argmax(ctx, ng, max_new, eot, s0, gs);
+        if (e1 == cudaSuccess) e1 = cudaEventRecord(ctx->dec_group_done[g], gs);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(st, ctx->dec_group_done[g], 0);
+      }
+    }
+    if (rc == WB_OK && e1 == cudaSuccess) e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
     cudaError_t e3 = cudaStreamEndCapture(st, &graph);
     if (rc != WB_OK) return rc;
     if (e1 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "argmax (capture)", e1);
@@ -461,6 +527,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     ctx->step_graph_eot = eot;
     ctx->step_graph_enc_T = enc_T;
     ctx->step_graph_n_split = n_split;
+    ctx->step_graph_groups = n_groups;
   }
   std::vector<int> done_h(n_seqs, 0);
   for (int it = 0; it < n_steps_max; ++it) {
@@ -469,7 +536,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
       WB_CK(cudaGraphLaunch(ctx->step_graph, st));
       // per layer: 6 linear + self-attn + cross-attn (LayerNorm folded into the linears); + embed, final LN,
       // logits, arg-max, advance
-      ctx->tm.n_kernel_launches += 8 * hp.n_text_layer + 5;
+      ctx->tm.n_kernel_launches += (8 * hp.n_text_layer + 4) * (n_groups > 1 ? (n_seqs + per_group - 1) / per_group : 1) + 1;
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");

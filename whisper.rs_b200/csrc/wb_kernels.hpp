@@ -172,7 +172,7 @@ cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long ro
 // D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
                          const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats = nullptr,
-                         __half* x16 = nullptr, int n_clear = 0);
+                         __half* x16 = nullptr, int n_clear_slots = 0);
 // D2: append this step's K/V to the F16 cache [seq][n_text_ctx][d], causal attention over it
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
                                     const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st);

@@ -87,6 +87,47 @@ def transcribe_clip(ctx: api.WhisperContext, pcm: np.ndarray, *, rank: int = 0, 
     return part.windows, toks, lens, marg
 
 
+def conditioned_prompt(ctx: api.WhisperContext, prompt_past: Sequence[int], prompt_init: Sequence[int]) -> List[int]:
+    """The prompt of a window that follows decoded text -- `prompt_past` of WhisperContext (src/main.rs:356; never
+    written by the reference, whose decode loop does not exist) with upstream whisper.cpp v1.0.3's rule, the code
+    base main.rs transliterates: [token_prev] + the last n_text_ctx / 2 tokens of the text decoded so far, then the
+    initial prompt ([sot] ...).  No past text: the initial prompt alone."""
+    if not prompt_past:
+        return list(prompt_init)
+    n_take = min(ctx.n_text_ctx // 2, len(prompt_past))
+    return [ctx.token_prev] + [int(t) for t in prompt_past[len(prompt_past) - n_take:]] + list(prompt_init)
+
+
+def transcribe_long_form(ctx: api.WhisperContext, pcm: np.ndarray, *, prompt_init: Optional[Sequence[int]] = None,
+                         max_new: int = 224, eot: Optional[int] = None, condition_on_previous: bool = True):
+    """Long-form decoding with `prompt_past` (src/main.rs:356): the windows of one clip are decoded IN ORDER and window
+    w's prompt carries the tokens decoded for the windows before it (conditioned_prompt).  This makes the windows of
+    a clip sequential: the mel is computed once for the clip, then encode + greedy decode run
+    window after window -- independent clips, not windows, are the unit of parallelism here.
+    Returns (tokens per window [list of int32 arrays], prompts used per window)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    fpw = 2 * ctx.audio_ctx
+    n_win = n_windows(pcm.size, fpw)
+    api.whisper_pcm_to_mel(ctx, pcm)
+    init = list(prompt_init) if prompt_init is not None else default_prompt(ctx)
+    eot_id = ctx.token_eot if eot is None else eot
+    past: List[int] = []
+    out, prompts = [], []
+    for w in range(n_win):
+        api.whisper_encode(ctx, 1, w * fpw)                    # the reference's call (2074) at this window's offset
+        prompt = conditioned_prompt(ctx, past, init) if condition_on_previous else list(init)
+        room = ctx.n_text_ctx - len(prompt)
+        t, _, l = api.whisper_decode_greedy(ctx, prompt, min(max_new, room), n_seqs=1, eot=eot_id)
+        ids = t[0][: int(l[0])]
+        out.append(ids.copy())
+        prompts.append(prompt)
+        if condition_on_previous:
+            # upstream keeps what it took plus the new tokens: the text decoded so far, newest last
+            taken = prompt[1:len(prompt) - len(init)] if len(prompt) > len(init) else []
+            past = taken + [int(x) for x in ids if int(x) != eot_id]
+    return out, prompts
+
+
 class WhisperTokenData:
     """WhisperTokenData (src/main.rs:317-331): id, the time-stamp token it implies (tid), and the window-relative
     times a time-stamp id carries (t0 / t1 in units of 10 ms, as upstream: id - token_beg steps of 20 ms).  The
