@@ -103,3 +103,24 @@ def test_mel_prefetched_upload(pkg, ctx):
     api.whisper_pcm_prefetch_ptr(ctx, a.ctypes.data, a.nbytes)   # prefetched but not consumed ...
     api.whisper_pcm_to_mel_ptr(ctx, b.ctypes.data, b.size, 1)    # ... a different buffer is copied normally
     np.testing.assert_array_equal(ctx.mel(0), ref_b)
+
+
+def test_mel_clips_shorter_than_one_window(pkg, pyoracle, model_path, ctx):
+    """n_len = n_samples / 160 (src/main.rs:1575): clips shorter than one FFT window (400 samples) still yield their
+    frames (zero-filled past the end, 1596-1600); fewer than 160 samples yield no frame at all, and encoding such a
+    clip encodes an all-zero window (1816-1829)."""
+    from whisper_rs_b200 import api
+    orc = pyoracle.Oracle(model_path("micro"))
+    for n in (160, 161, 399, 400, 479, 480):
+        pcm = pkg.synth.make_segment(13, 1000, 0.0)[:n].copy()
+        api.whisper_pcm_to_mel(ctx, pcm)
+        ref = orc.pcm_to_mel(pcm)
+        got = ctx.mel(0)
+        assert got.shape == ref.shape == (80, n // 160), n
+        assert mel_close(got, ref), n
+    pcm = pkg.synth.make_segment(13, 1000, 0.0)[:100].copy()       # no frame
+    api.whisper_pcm_to_mel(ctx, pcm)
+    assert ctx.mel(0).shape == (80, 0)
+    api.whisper_encode(ctx, 1, 0)
+    orc.pcm_to_mel(pcm)
+    assert rel_l2(ctx.encoder_out(0), orc.encode(0)) < 1e-2
