@@ -298,7 +298,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     // thread; software-pipelining the next step's TMEM load and max under the exponentials; requesting the
     // next step's scores into each half of the score registers as soon as its exponentials are done -- no
     // extra registers, but 579 -> 525 TFLOP/s: the barrier wait + fence + tcgen05.ld in mid-step stall the
-    // exponential stream more than the early data saves.)
+    // exponential stream more than the early data saves.  Round 2: a SPECULATIVE exponent -- this step's exponentials
+    // with the previous steps' offset, the row max computed beside them and used only to decide whether the step must
+    // be redone -- takes the max off the dependency chain but holds both P halves in registers (115 -> 164): 485 -> 468
+    // TFLOP/s at whisper medium, 64 segments; with 7 of 16 pairs on the FMA pipe as well 445; 7 of 16 without
+    // speculation 494, i.e. flat.)
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int sb = j & 1;
@@ -320,35 +324,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
           if (kbase + 32 + i >= T) s1[i] = 0xff800000u;
         }
       }
-#ifdef WB_ATTN_SPEC
-      // Speculative exponent (experiment): the exponentials of this step use the offset of the PREVIOUS steps, so
-      // they do not wait for this step's row max; the max is computed beside them and only decides whether the step
-      // has to be redone with a new offset (rare after the first steps: the lazy threshold is 2^8).
-      uint32_t p0[16], p1[16];
-      bool first = true;
-      for (;;) {
-        if (j > 0 || !first) {
-          const float moff_s = m_used * c;
-          const uint64_t m2s = f2_pack(-moff_s, -moff_s);
-          exp_chunk(s0, c2, m2s, p0, K);
-          exp_chunk(s1, c2, m2s, p1, K);
-        }
-        if (!first) break;
-        first = false;
-        const float mx = fmaxf(max_chunk(s0), max_chunk(s1));
-        const bool grow = (mx - m_used) * c > RESCALE_LOG2;   // true on the first step (m_used = -inf)
-        if (!__any_sync(0xffffffffu, grow)) break;
-        if (j > 0) {
-          mbar_wait(&bar_o[g], (j - 1) & 1);   // P_{j-1} V_{j-1} retired: O is idle until P_j is handed over
-          __syncwarp();
-          tc_fence_after();
-          rescale_o(twg + TMEM_O, grow ? exp2f((m_used - mx) * c) : 1.0f);
-        }
-        if (grow) m_used = mx;
-      }
-      tmem_st_32x32b_x16(my_s, p0);
-      tmem_st_32x32b_x16(my_s + 16, p1);
-#else
       const float mx = fmaxf(max_chunk(s0), max_chunk(s1));
       ATTN_TRACE((j * 2 + g) * 8 + 2);
       // ---- lazy running max: rescale O only when this row's max grew by more than 2^8
@@ -372,7 +347,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
         exp_chunk(s1, c2, m2, p, K);
         tmem_st_32x32b_x16(my_s + 16, p);
       }
-#endif
       tmem_st_wait();
       tc_fence_before();   // TMEM accesses ordered before the MMAs the MMA warp issues
       __syncwarp();

@@ -597,11 +597,6 @@ cudaError_t launch_bn(const GemmProblem& g, const Gemm2Args& a, int grid, cudaSt
 
 }  // namespace
 
-bool gemm2_setup_attributes(const char** err) {
-  (void)err;   // each instantiation opts in to its shared-memory size at its first launch (launch_one)
-  return true;
-}
-
 // pair tile width: widest of 256 / 192 / 128 / 64 that divides N; 0 = not eligible (use gemm.cu)
 int gemm2_pick_bn(int N) {
   if (N % 256 == 0) return 256;

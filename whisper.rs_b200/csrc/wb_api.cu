@@ -669,7 +669,7 @@ int wb_ctx_create(const char* model_path, const wb_config* cfg_in, wb_ctx** out)
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->ev[i][j]);
   const char* aerr = "";
-  if (!gemm_setup_attributes(&aerr) || !gemm2_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
+  if (!gemm_setup_attributes(&aerr) || !attention_setup_attributes(&aerr)) {
     fail_msg(ctx, WB_ERR_TENSOR_OP, std::string("galois tensor:'kernel attribute setup: ") + aerr + "'");
     return bail(WB_ERR_TENSOR_OP);
   }

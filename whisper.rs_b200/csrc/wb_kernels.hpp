@@ -105,7 +105,6 @@ int gemm_pick_bn(int N);
 bool gemm_setup_attributes(const char** err);
 cudaError_t launch_gemm2(const GemmProblem& g, int num_sms, cudaStream_t st);
 int gemm2_pick_bn(int N);   // 0: N not eligible for the pair kernel
-bool gemm2_setup_attributes(const char** err);
 
 // ---- fused softmax attention (galois_flash_attn src/main.rs:1787-1797, call 1922) -------------
 constexpr int ATTN_VT_HEAD_ROWS = 80;   // 64 head rows + 1 row of ones + 15 zero rows (MMA N = 80)

@@ -1,7 +1,8 @@
 //! Raw bindings: one `extern "C"` item per declaration of include/whisper_b200.h, in the same
 //! order.  NOT COMPILED in the build image (no Rust toolchain there); the same symbols are
 //! exercised through ctypes (whisper.rs_b200/cabi.py) and checked by
-//! tests/test_host.py::test_cabi_exports_every_declared_symbol.
+//! tests/test_host.py::test_cabi_exports_every_declared_symbol; a compiled C consumer of the same header
+//! (tests/c/main_replay.c) replays the reference's `fn main` against the library on the GPU box.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -87,4 +88,13 @@ extern "C" {
     pub fn wb_timings_get(ctx: *const wb_ctx, out: *mut wb_timings) -> c_int;
     pub fn wb_last_error(ctx: *const wb_ctx) -> *const c_char;
     pub fn wb_version() -> *const c_char;
+    /// guard zones around every device buffer (wb_config.reserved[1] = 1): number of zones written into, -1 = no guards
+    pub fn wb_dbg_canary_check(ctx: *mut wb_ctx) -> c_int;
 }
+
+// Layout the C compiler gives the two structs (tests/c/abi_layout.c prints it; tests/test_host.py asserts the ctypes
+// mirror against it).  A Rust build checks the same numbers at compile time.
+const _: () = {
+    assert!(std::mem::size_of::<wb_config>() == 72);
+    assert!(std::mem::size_of::<wb_timings>() == 72);
+};
