@@ -332,3 +332,28 @@ def test_no_kernel_writes_outside_its_buffers(pkg, model_path, arch):
     plain = api.WhisperContext.new(model_path(arch), max_segments=1, decode_capacity=False)
     assert plain.canary_check() == -1                     # no guards unless asked for
     plain.close()
+
+
+def test_decoder_bit_reproducible(pkg, model_path):
+    """The decode step carries no floating-point atomics either (the folded LayerNorm statistics are accumulated as
+    64-bit fixed-point integers): logits, greedy ids and margins of repeated runs are identical bit for bit -- which is
+    what lets a clip split over several GPUs reproduce the single-GPU ids exactly (tools/run_config5.py)."""
+    from whisper_rs_b200 import api
+    B = 5
+    ctx = api.WhisperContext.new(model_path("tiny"), max_segments=B, max_clips=B)
+    clips = pkg.synth.make_clips(B, first_seg=640)
+    api.whisper_pcm_to_mel(ctx, clips)
+    api.whisper_encode(ctx, 1, [0] * B, clip_ids=list(range(B)))
+    prompt = np.tile(np.array([ctx.token_sot, 11, 12], dtype=np.int32), (B, 1))
+    ref_logits, ref_greedy = None, None
+    for rep in range(3):
+        api.whisper_decode(ctx, prompt, 0)                        # many-row prompt pass (LayerNorm kernel path)
+        api.whisper_decode(ctx, prompt[:, :1], 3)                 # single-token step (folded statistics)
+        lg = np.stack([ctx.logits(s) for s in range(B)])
+        toks, marg, lens = api.whisper_decode_greedy(ctx, [ctx.token_sot], 40, n_seqs=B, eot=-1)
+        if rep == 0:
+            ref_logits, ref_greedy = lg, (toks.copy(), marg.copy(), lens.copy())
+        else:
+            assert np.array_equal(lg, ref_logits), rep
+            assert np.array_equal(toks, ref_greedy[0]) and np.array_equal(marg, ref_greedy[1]) and np.array_equal(lens, ref_greedy[2]), rep
+    ctx.close()

@@ -37,6 +37,14 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   return r;
 }
 
+// (sum, sum of squares) -> the fixed-point form the folded LayerNorm statistics are accumulated in
+__device__ __forceinline__ DecLnStat dec_ln_fixed(float s1, float s2) {
+  DecLnStat r;
+  r.s1 = (unsigned long long)__float2ll_rn(s1 * DEC_LN_S1_SCALE);
+  r.s2 = (unsigned long long)__float2ll_rn(s2 * DEC_LN_S2_SCALE);
+  return r;
+}
+
 __device__ __forceinline__ float block_max(float v, float* sh, int n_warps) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -64,7 +72,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
 // atomics; another sequence group's rows of the same slots may be in use on another stream).
 __global__ void __launch_bounds__(128)
 embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
-             int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, float2* __restrict__ stats,
+             int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, DecLnStat* __restrict__ stats,
              __half* __restrict__ x16, int n_clear_slots) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
@@ -94,11 +102,11 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
     }
     __syncthreads();
     if (threadIdx.x == 0)
-      stats[row] = make_float2((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]), (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+      stats[row] = dec_ln_fixed((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]), (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
     if (blockIdx.x == 0) {
       const int rows = gridDim.x;
       for (int c = threadIdx.x; c < n_clear_slots * rows; c += blockDim.x)
-        stats[(size_t)(1 + c / rows) * DEC_LN_ROWS + c % rows] = make_float2(0.0f, 0.0f);
+        stats[(size_t)(1 + c / rows) * DEC_LN_ROWS + c % rows] = DecLnStat{0ull, 0ull};
     }
   }
 }
@@ -511,7 +519,7 @@ decode_linear_kernel(const DecodeLinear a) {
   pdl_wait();   // the activations (and the residual) are the previous kernel's output
   // residual row segment and row statistics: requested now, used after the MMAs
   float4 e_res = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 e_st = make_float2(0.f, 0.f);
+  DecLnStat e_st{0ull, 0ull};
   if (a.residual && er < a.R && evec && (a.res_ld & 3) == 0)
     e_res = *reinterpret_cast<const float4*>(a.residual + (size_t)er * a.res_ld + n0 + ef0);
   if (a.ln_in) e_st = a.ln_in[min(er, a.R - 1)];
@@ -585,9 +593,11 @@ decode_linear_kernel(const DecodeLinear a) {
   //   rstd * (x w^T - mu * c1) + c2, c2 in the bias slot
   float ln_rstd = 1.0f, ln_nmr = 0.0f;
   if (a.ln_in) {
-    const float mu = e_st.x * a.ln_inv_d;
-    ln_rstd = rsqrtf(fmaxf(e_st.y * a.ln_inv_d - mu * mu, 0.0f) + a.ln_eps);
-    ln_nmr = -mu * ln_rstd;
+    // exact integer sums -> f64 for the mean / variance (E[x^2] - mu^2 in f64: no cancellation to speak of)
+    const double mu = (double)(long long)e_st.s1 * (1.0 / (double)DEC_LN_S1_SCALE) * (double)a.ln_inv_d;
+    const double ex2 = (double)(long long)e_st.s2 * (1.0 / (double)DEC_LN_S2_SCALE) * (double)a.ln_inv_d;
+    ln_rstd = rsqrtf((float)fmax(ex2 - mu * mu, 0.0) + a.ln_eps);
+    ln_nmr = -(float)mu * ln_rstd;
   }
   if (evec && (!a.residual || (a.res_ld & 3) == 0)) {   // whole 4-feature group inside N: the prefetched constants
     const float bb[4] = {e_bias.x, e_bias.y, e_bias.z, e_bias.w}, c1[4] = {e_c1.x, e_c1.y, e_c1.z, e_c1.w};
@@ -657,9 +667,10 @@ decode_linear_kernel(const DecodeLinear a) {
     s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
     s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
     if (r < a.R) {
-      if ((tid & 3) == 0) {
-        atomicAdd(&a.ln_out[r].x, s1);
-        atomicAdd(&a.ln_out[r].y, s2);
+      if ((tid & 3) == 0) {   // integer atomics: the sum does not depend on the order the CTAs arrive in
+        const DecLnStat f = dec_ln_fixed(s1, s2);
+        atomicAdd(&a.ln_out[r].s1, f.s1);
+        atomicAdd(&a.ln_out[r].s2, f.s2);
       }
       if (n0 + f0 + 3 < a.N) {
         uint2 u;
@@ -762,7 +773,7 @@ __global__ void advance_kernel(int* n_past, int add, int* step) {
 }  // namespace
 
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
-                         const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats, __half* x16,
+                         const int* n_past_dev, int d, float* x, cudaStream_t st, DecLnStat* stats, __half* x16,
                          int n_clear_slots) {
   if (stats && n_seq * n_tok > DEC_LN_ROWS) return cudaErrorInvalidValue;
   return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x, stats,

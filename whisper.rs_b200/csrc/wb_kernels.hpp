@@ -39,6 +39,15 @@ bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ---- GEMM: C[b][m][n] = epi( sum_k A[b][m][k] * W[n][k] ), f16 x f16 -> f32 (TMEM) -------------
 // Restates galois_matmul (src/main.rs:1752-1767) / galois_conv_1d_* (1709-1721) call sites with
 // their bias / scale / GELU / residual / F16-repack followers fused into the epilogue.
+// Row statistics of the decoder's folded LayerNorms: sum(x) * 2^30 and sum(x^2) * 2^20 as signed 64-bit integers
+// (two's complement in unsigned words for atomicAdd).  |sum x| < 8e9 and sum x^2 < 8e12 fit; the quantisation (1e-9 /
+// 1e-6 absolute) is far below the f32 rounding of the terms themselves.
+struct DecLnStat {
+  unsigned long long s1, s2;
+};
+constexpr float DEC_LN_S1_SCALE = 1073741824.0f;   // 2^30
+constexpr float DEC_LN_S2_SCALE = 1048576.0f;      // 2^20
+
 struct GemmEpilogue {
   const float* bias = nullptr;      // [N] added to the accumulator
   const float* colscale = nullptr;  // [N] multiplies (acc + bias)
@@ -75,11 +84,13 @@ struct GemmEpilogue {
   const float2* ln_part_in = nullptr;
   int ln_parts = 0;
   float* ln_center = nullptr;
-  // the same fold in the decoder's single-token step (decode_kernels.cu): per-row (sum, sum of squares) of x
-  float2* ln_stats_out = nullptr;
+  // the same fold in the decoder's single-token step (decode_kernels.cu): per-row (sum, sum of squares) of x as
+  // 64-bit FIXED-POINT numbers (DecLnStat), so that the atomic accumulation over CTAs is exact integer addition and the
+  // result does not depend on the order the CTAs arrive in
+  DecLnStat* ln_stats_out = nullptr;
   __half* x16_out = nullptr;
   int x16_ld = 0;
-  const float2* ln_stats_in = nullptr;
+  const DecLnStat* ln_stats_in = nullptr;
   float ln_eps = 1e-5f;
   // swap-AB mode for skinny activations (decoder): the GEMM computes C^T; element (m, n) is
   // stored at out[n*out_ld + m] and bias/colscale/residual are indexed by m instead of n.
@@ -170,7 +181,7 @@ cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long ro
 // n_past / step live in device memory so one captured CUDA graph serves every position.
 // D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
-                         const int* n_past_dev, int d, float* x, cudaStream_t st, float2* stats = nullptr,
+                         const int* n_past_dev, int d, float* x, cudaStream_t st, DecLnStat* stats = nullptr,
                          __half* x16 = nullptr, int n_clear_slots = 0);
 // D2: append this step's K/V to the F16 cache [seq][n_text_ctx][d], causal attention over it
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
@@ -199,10 +210,10 @@ struct DecodeLinear {
   int out_f16 = 1, out_ld = 0;
   float* top2 = nullptr;           // optional [R][n_parts][3]: per-CTA (top value, second value, index bits)
   // LayerNorm folded into the single-token step (no LayerNorm kernels between the linears):
-  const float2* ln_in = nullptr;   // consumer: per-row (sum, sum of squares) of x; w carries gamma, bias = c2
+  const DecLnStat* ln_in = nullptr;   // consumer: per-row (sum, sum of squares) of x (fixed point); w carries gamma, bias = c2
   const float* ln_c1 = nullptr;    //           c1[n] = sum_k w[n][k]
   float ln_inv_d = 0.0f, ln_eps = 1e-5f;
-  float2* ln_out = nullptr;        // producer: statistics of the f32 result rows, accumulated atomically
+  DecLnStat* ln_out = nullptr;     // producer: statistics of the f32 result rows, accumulated with integer atomics
   __half* x16_out = nullptr;       //           and their F16 copy [R][x16_ld] (the next linear's activations)
   int x16_ld = 0;
 };
