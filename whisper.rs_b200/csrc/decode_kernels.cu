@@ -377,6 +377,20 @@ struct Top2 {
   float v1, v2;
   int i1;
 };
+
+// End-of-step bookkeeping folded into the arg-max kernel (one launch less per token): every block has read the step
+// counter before it arrives here, and the block that arrives last moves n_past / step on for the next step.
+// n_past_p[0] = n_past, [1] = step, [2] = arrival counter (self-resetting).  n_past_p == nullptr: leave them alone.
+__device__ __forceinline__ void step_advance(int* step_p, int* n_past_p, int advance_by) {
+  if (!n_past_p) return;
+  __threadfence();
+  const int old = atomicAdd(&n_past_p[2], 1);
+  if (old == (int)gridDim.x - 1) {
+    n_past_p[0] += advance_by;
+    *step_p += 1;
+    n_past_p[2] = 0;
+  }
+}
 __device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
   Top2 r;
   if (b.v1 > a.v1 || (b.v1 == a.v1 && b.i1 < a.i1)) {
@@ -394,7 +408,8 @@ __device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ next_tok, float* __restrict__ margin_out,
               int* __restrict__ out_tokens, float* __restrict__ out_margin, int* __restrict__ out_len,
-              int* __restrict__ done, int max_new, const int* __restrict__ step_p, int eot) {
+              int* __restrict__ done, int max_new, int* __restrict__ step_p, int eot, int* __restrict__ n_past_p,
+              int advance_by) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ Top2 sh[32];
@@ -435,6 +450,7 @@ argmax_kernel(const float* __restrict__ logits, int n_vocab, int* __restrict__ n
         if (r.i1 == eot) done[s] = 1;
       }
     }
+    step_advance(step_p, n_past_p, advance_by);
   }
 }
 
@@ -722,8 +738,8 @@ decode_linear_kernel(const DecodeLinear a) {
 __global__ void __launch_bounds__(256)
 argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restrict__ next_tok,
                        float* __restrict__ margin_out, int* __restrict__ out_tokens, float* __restrict__ out_margin,
-                       int* __restrict__ out_len, int* __restrict__ done, int max_new, const int* __restrict__ step_p,
-                       int eot) {
+                       int* __restrict__ out_len, int* __restrict__ done, int max_new, int* __restrict__ step_p,
+                       int eot, int* __restrict__ n_past_p, int advance_by) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ Top2 sh[8];
@@ -758,6 +774,7 @@ argmax_partials_kernel(const float* __restrict__ part, int n_part, int* __restri
         if (r.i1 == eot) done[s] = 1;
       }
     }
+    step_advance(step_p, n_past_p, advance_by);
   }
 }
 
@@ -806,10 +823,10 @@ cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, co
 }
 
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
-                          float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
-                          cudaStream_t st) {
+                          float* out_margin, int* out_len, int* done, int max_new, int* step_dev, int eot,
+                          cudaStream_t st, int* n_past_dev, int advance_by) {
   argmax_kernel<<<n_seq, 1024, 0, st>>>(logits, n_vocab, next_tok, margin, out_tokens, out_margin, out_len, done,
-                                        max_new, step_dev, eot);
+                                        max_new, step_dev, eot, n_past_dev, advance_by);
   return cudaGetLastError();
 }
 
@@ -842,9 +859,9 @@ int decode_linear_parts(int N) { return (N + DL_ROWS - 1) / DL_ROWS; }
 
 cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
                                    int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
-                                   const int* step_dev, int eot, cudaStream_t st) {
+                                   int* step_dev, int eot, cudaStream_t st, int* n_past_dev, int advance_by) {
   return launch_pdl(argmax_partials_kernel, dim3(n_seq), dim3(256), 0, st, part, n_part, next_tok, margin, out_tokens,
-                    out_margin, out_len, done, max_new, step_dev, eot);
+                    out_margin, out_len, done, max_new, step_dev, eot, n_past_dev, advance_by);
 }
 
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st) {

@@ -350,17 +350,20 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
 }
 
 // D6 bookkeeping after a decode pass: from the top-2 partials when the skinny logits kernel ran
-static cudaError_t run_argmax(wb_ctx* ctx, int n_seqs, int max_new, int eot, int seq0 = 0, cudaStream_t st = nullptr) {
+// advance_by > 0: the kernel also moves n_past / step on once every sequence is done (no separate advance launch)
+static cudaError_t run_argmax(wb_ctx* ctx, int n_seqs, int max_new, int eot, int seq0 = 0, cudaStream_t st = nullptr,
+                              int advance_by = 0) {
   const ModelHParams& hp = ctx->hp;
   if (!st) st = ctx->stream;
   const size_t o = (size_t)seq0, om = (size_t)seq0 * max_new;   // this group's sequences
   if (ctx->logits_top2_valid)
     return launch_argmax_partials(ctx->d_top2 + o * decode_linear_parts(hp.n_vocab) * 3, decode_linear_parts(hp.n_vocab), n_seqs,
                                   ctx->d_next + o, ctx->d_margin + o, ctx->d_out_tokens + om, ctx->d_out_margin + om,
-                                  ctx->d_out_len + o, ctx->d_done + o, max_new, ctx->d_step, eot, st);
+                                  ctx->d_out_len + o, ctx->d_done + o, max_new, ctx->d_step, eot, st,
+                                  advance_by > 0 ? ctx->d_npast : nullptr, advance_by);
   return launch_argmax(ctx->d_logits + o * hp.n_vocab, n_seqs, hp.n_vocab, ctx->d_next + o, ctx->d_margin + o,
                        ctx->d_out_tokens + om, ctx->d_out_margin + om, ctx->d_out_len + o, ctx->d_done + o, max_new, ctx->d_step,
-                       eot, st);
+                       eot, st, advance_by > 0 ? ctx->d_npast : nullptr, advance_by);
 }
 
 static int check_decode_args(wb_ctx* ctx, int n_tok, int n_past, int n_seq) {
@@ -444,8 +447,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
   if ((rc = decode_pass(ctx, ctx->d_tokens, n_seqs, n_prompt))) return rc;
   {
     LaunchTimer t(ctx, "dec_argmax");
-    WB_CK(run_argmax(ctx, n_seqs, max_new, eot));
-    WB_CK(launch_advance(ctx->d_npast, n_prompt, ctx->d_step, st));
+    WB_CK(run_argmax(ctx, n_seqs, max_new, eot, 0, nullptr, n_prompt));   // + n_past += n_prompt, step = 1
   }
   WB_CK(cudaStreamSynchronize(st));   // `toks` is a stack temporary
   // ---- single-token steps: captured once, replayed for every position
@@ -498,7 +500,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
     if (n_groups <= 1) {
       rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
-      if (rc == WB_OK) e1 = run_argmax(ctx, n_seqs, max_new, eot);
+      if (rc == WB_OK) e1 = run_argmax(ctx, n_seqs, max_new, eot, 0, nullptr, 1);   // + the step's bookkeeping
     } else {
       // fork: every branch starts behind the previous step's bookkeeping on `st`; join: `st` waits for every branch
       e1 = cudaEventRecord(ctx->dec_fork, st);
@@ -513,7 +515,7 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
         if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(st, ctx->dec_group_done[g], 0);
       }
     }
-    if (rc == WB_OK && e1 == cudaSuccess) e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
+    if (rc == WB_OK && e1 == cudaSuccess && n_groups > 1) e2 = launch_advance(ctx->d_npast, 1, ctx->d_step, st);
     cudaError_t e3 = cudaStreamEndCapture(st, &graph);
     if (rc != WB_OK) return rc;
     if (e1 != cudaSuccess) return fail(ctx, WB_ERR_TENSOR_OP, "argmax (capture)", e1);
@@ -536,12 +538,11 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
       WB_CK(cudaGraphLaunch(ctx->step_graph, st));
       // per layer: 6 linear + self-attn + cross-attn (LayerNorm folded into the linears); + embed, final LN,
       // logits, arg-max, advance
-      ctx->tm.n_kernel_launches += (8 * hp.n_text_layer + 4) * (n_groups > 1 ? (n_seqs + per_group - 1) / per_group : 1) + 1;
+      ctx->tm.n_kernel_launches += (8 * hp.n_text_layer + 4) * (n_groups > 1 ? (n_seqs + per_group - 1) / per_group : 1) + (n_groups > 1 ? 1 : 0);
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");
-      WB_CK(run_argmax(ctx, n_seqs, max_new, eot));
-      WB_CK(launch_advance(ctx->d_npast, 1, ctx->d_step, st));
+      WB_CK(run_argmax(ctx, n_seqs, max_new, eot, 0, nullptr, 1));
     }
     n_past += 1;
     if ((it & 31) == 31) {   // every 32 steps: stop early once every sequence has emitted eot

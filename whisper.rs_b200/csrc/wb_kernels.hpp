@@ -193,8 +193,8 @@ cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, co
                                      float* part_o, float* part_ml, int n_split, int* split_cnt, cudaStream_t st);
 // D6 / K13: per-sequence arg-max + top-2 margin + greedy-loop bookkeeping
 cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next_tok, float* margin, int* out_tokens,
-                          float* out_margin, int* out_len, int* done, int max_new, const int* step_dev, int eot,
-                          cudaStream_t st);
+                          float* out_margin, int* out_len, int* done, int max_new, int* step_dev, int eot,
+                          cudaStream_t st, int* n_past_dev = nullptr, int advance_by = 0);   // n_past_dev: also advance n_past / step
 // skinny linear layer of a decode step (R <= 32 activation rows): out[r][n] = epi(sum_k x[r][k] W[n][k])
 struct DecodeLinear {
   const __half* w = nullptr;       // [N][K] f16, K contiguous
@@ -222,7 +222,7 @@ cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st);
 int decode_linear_parts(int N);    // CTAs (= top-2 partials per sequence) for N output features
 cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
                                    int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
-                                   const int* step_dev, int eot, cudaStream_t st);
+                                   int* step_dev, int eot, cudaStream_t st, int* n_past_dev = nullptr, int advance_by = 0);
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st);
 
 }  // namespace wb
