@@ -208,3 +208,43 @@ def test_special_tokens_follow_the_language_count(pkg, pyoracle, tmp_path):
         o = pyoracle.Oracle(p)
         assert (o.token_eot, o.token_sot, o.token_prev, o.token_solm, o.token_not, o.token_beg, o.token_translate,
                 o.token_transcribe) == ids, nv
+
+
+def test_cpp_host_header_error_behaviour(pkg, model_path, tmp_path):
+    """include/whisper_b200.hpp (the C++ host side with the reference's names) compiled with g++ -std=c++17 -pedantic:
+    every loader failure arrives as the reference's WsError variant with its Display text (src/main.rs:50-72), and
+    without a B200 `WhisperContext::new_` throws WrongGTensor instead of computing on the CPU."""
+    import subprocess
+    import torch
+    from whisper_rs_b200 import cabi
+    cabi.build()
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.run(["make", "-C", cdir, "reference_main"], check=True, stdout=subprocess.DEVNULL)
+    exe = os.path.join(cdir, "reference_main")
+    good = open(model_path("micro"), "rb").read()
+    mf = pkg.ggml_file.read_model(model_path("micro"))
+    d = tmp_path / "bad"
+    d.mkdir()
+    (d / "bad_magic.bin").write_bytes(b"\x01\x02\x03\x04" + good[4:])
+    t = dict(mf.tensors)
+    t["encoder.bogus.weight"] = np.zeros((4,), np.float32)
+    pkg.ggml_file.write_model(str(d / "unknown.bin"), mf.hparams, 0, tensors=t)
+    t = dict(mf.tensors)
+    t["encoder.ln_post.weight"] = np.ones((mf.hparams.n_audio_state + 1,), np.float32)
+    pkg.ggml_file.write_model(str(d / "size.bin"), mf.hparams, 0, tensors=t)
+    t = dict(mf.tensors)
+    t["encoder.blocks.0.mlp.0.weight"] = t["encoder.blocks.0.mlp.0.weight"].T.copy()
+    pkg.ggml_file.write_model(str(d / "shape.bin"), mf.hparams, 0, tensors=t)
+    t = dict(mf.tensors)
+    t["encoder.blocks.0.mlp.0.weight"] = t["encoder.blocks.0.mlp.0.weight"].astype(np.float32)
+    pkg.ggml_file.write_model(str(d / "bytes.bin"), mf.hparams, 0, tensors=t)
+    r = subprocess.run([exe, "--errors", str(d)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.count(" ok") == 6 and "UNEXPECTED" not in r.stdout
+    for variant in ("BadMagic", "UnexpectIO", "UnknownTensor", "WrongSizeTensor", "WrongShapeTensor", "WrongBytesTensor"):
+        assert variant in r.stdout
+    if not torch.cuda.is_available():
+        pcm = tmp_path / "pcm.raw"
+        np.zeros(16000, np.int16).tofile(str(pcm))
+        r = subprocess.run([exe, model_path("micro"), str(pcm), str(tmp_path / "o")], capture_output=True, text=True)
+        assert r.returncode == 10 and r.stderr.startswith("WrongGTensor:") and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)

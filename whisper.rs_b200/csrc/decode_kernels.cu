@@ -101,11 +101,12 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
       red[1][threadIdx.x >> 5] = s2;
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0)   // this slot's sub-slot 0 holds the whole row; its other sub-slots are cleared below
       stats[row] = dec_ln_fixed((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]), (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
     if (blockIdx.x == 0) {
       const int rows = gridDim.x;
-      for (int c = threadIdx.x; c < n_clear_slots * rows; c += blockDim.x)
+      // sub-slots 1 .. of slot 0 and every sub-slot of the n_clear_slots slots behind it, this launch's rows only
+      for (int c = threadIdx.x; c < ((1 + n_clear_slots) * DEC_LN_SUB - 1) * rows; c += blockDim.x)
         stats[(size_t)(1 + c / rows) * DEC_LN_ROWS + c % rows] = DecLnStat{0ull, 0ull};
     }
   }
@@ -538,7 +539,15 @@ decode_linear_kernel(const DecodeLinear a) {
   DecLnStat e_st{0ull, 0ull};
   if (a.residual && er < a.R && evec && (a.res_ld & 3) == 0)
     e_res = *reinterpret_cast<const float4*>(a.residual + (size_t)er * a.res_ld + n0 + ef0);
-  if (a.ln_in) e_st = a.ln_in[min(er, a.R - 1)];
+  if (a.ln_in) {   // the row's sub-slots, added as integers (any order gives the same sum)
+    const DecLnStat* sp = a.ln_in + min(er, a.R - 1);
+#pragma unroll
+    for (int u = 0; u < DEC_LN_SUB; ++u) {
+      const DecLnStat v = sp[u * DEC_LN_ROWS];
+      e_st.s1 += v.s1;
+      e_st.s2 += v.s2;
+    }
+  }
   if (pre) {
     uint4 X[U][4];
 #pragma unroll
@@ -685,8 +694,9 @@ decode_linear_kernel(const DecodeLinear a) {
     if (r < a.R) {
       if ((tid & 3) == 0) {   // integer atomics: the sum does not depend on the order the CTAs arrive in
         const DecLnStat f = dec_ln_fixed(s1, s2);
-        atomicAdd(&a.ln_out[r].s1, f.s1);
-        atomicAdd(&a.ln_out[r].s2, f.s2);
+        DecLnStat* dst = a.ln_out + (blockIdx.x & (DEC_LN_SUB - 1)) * DEC_LN_ROWS + r;
+        atomicAdd(&dst->s1, f.s1);
+        atomicAdd(&dst->s2, f.s2);
       }
       if (n0 + f0 + 3 < a.N) {
         uint2 u;

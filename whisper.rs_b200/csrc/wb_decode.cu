@@ -168,7 +168,7 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
     if ((rc = upload_f32_vec(ctx, ones, &ctx->d_ones))) return rc;
     if ((rc = upload_f32_vec(ctx, zeros, &ctx->d_zeros))) return rc;
   }
-  if ((rc = dev_alloc(ctx, &ctx->dec_ln_stats, (size_t)DEC_LN_ROWS * (3 * Lt + 1)))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->dec_ln_stats, (size_t)DEC_LN_SLOT * (3 * Lt + 1)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_npast, 4))) return rc;
   ctx->d_step = ctx->d_npast + 1;
   // split-K cross-attention partials (only used for few rows: n_tok <= 8)
@@ -225,7 +225,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
   // attn_ln, cross_attn_ln, mlp_ln of layer il).  Many rows (prompt pass on the tcgen05 GEMM): a LayerNorm
   // kernel without affine part in front of the same folded weights.
   const bool fold = R <= DEC_LN_ROWS && d % 64 == 0;
-  auto slot = [&](int i) { return ctx->dec_ln_stats + (size_t)i * DEC_LN_ROWS + r0; };
+  auto slot = [&](int i) { return ctx->dec_ln_stats + (size_t)i * DEC_LN_SLOT + r0; };
   {
     LaunchTimer t(ctx, "dec_embed");
     WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, dx, st,

@@ -218,6 +218,11 @@ struct DecodeLinear {
   int x16_ld = 0;
 };
 constexpr int DEC_LN_ROWS = 32;    // rows per statistics slot of the folded decode step
+// A slot is DEC_LN_SUB sub-slots of DEC_LN_ROWS rows: a producer CTA adds into sub-slot (its index mod DEC_LN_SUB), the
+// consumer adds the sub-slots up -- same-address atomics of the 48-320 CTAs of a producer serialise in L2 (measured:
+// one 64-bit word per row cost 0.36 us per producer kernel), spreading them over 4 words removes most of that.
+constexpr int DEC_LN_SUB = 4;
+constexpr int DEC_LN_SLOT = DEC_LN_SUB * DEC_LN_ROWS;
 cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st);
 int decode_linear_parts(int N);    // CTAs (= top-2 partials per sequence) for N output features
 cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int* next_tok, float* margin,
