@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_pipeline.py tests/test_gpu_cabi.py -m gpu -q -x --timeout 600 2>&1 | tail -3
-timeout 900 python -m pytest tests/test_gpu_parity_round2.py -m gpu -q -x --timeout 600 -k "decoder_bit or small_full or greedy_after or writes_outside" 2>&1 | tail -3
-for a in "small 32" "medium 32" "large-v3 15"; do timeout 300 python tools/dec_groups.py $a 224 2>&1 | tail -1; done
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_encoder.py -m gpu -q -x --timeout 600 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_parity_round2.py -m gpu -q -x --timeout 600 -k "base_batch16 or large_mean or full_depth" 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline --no-decoder --sustain-s 0 --steps 5 > gpurun_out/bench_resq.json 2> gpurun_out/bench_resq.err; echo "bench exit $?"; python tools/bench_brief.py gpurun_out/bench_resq.json

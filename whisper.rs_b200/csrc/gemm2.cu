@@ -353,6 +353,15 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
         uint8_t* sbuf = my_bufs + buf * EPI_BUF_BYTES;
         const uint32_t srow = smem_u32(sbuf) + lane * 128;
 
+        if (RES && lane == 0) {
+          // request the NEXT chunk's residual box now, a whole chunk ahead: its buffer was last read by the TMA store
+          // of chunk ci - 1, issued a moment ago (requesting it only after this chunk's store, as round 1 did, left
+          // ~400 cycles of lead against a ~1500-cycle L2 / HBM round trip -- the out-proj epilogue, 4 chunks per warp
+          // per 8192-cycle tile, was bound by that wait)
+          bulk_wait_group_read<0>();
+          issue_residual(ci + 1);
+        }
+
         // ---- accumulator chunk -> registers
         uint32_t r0[32], r1[32];
         if (!dead) {
@@ -510,15 +519,9 @@ gemm2_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap a_map, const __grid
           if (args.out_slab_cols > 0) tma_store_3d(&out_map, sbuf, n0 % args.out_slab_cols, m_row0, n0 / args.out_slab_cols);
           else tma_store_3d(&out_map, sbuf, n0, m_row0, it.b);
           bulk_commit_group();
-          if (RES) {
-            // prefetch the next chunk's residual into the other buffer once the store that last
-            // read it (chunk ci - 1) has drained; the store just issued may stay in flight
-            bulk_wait_group_read<1>();
-            issue_residual(ci + 1);
-          }
         }
         __syncwarp();
-        G2_TRACE(tre, 256 + t * 16 + 5 + k * 4);   // store issued (+ residual prefetch)
+        G2_TRACE(tre, 256 + t * 16 + 5 + k * 4);   // store issued
       }
       if (LN == 1 && my_nch > 0 && ln_m < args.M_rows) {
         float a0, a1, b0, b1;
