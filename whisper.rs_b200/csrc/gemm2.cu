@@ -15,7 +15,10 @@
 // for a TMA-store epilogue.
 //
 // Roles per CTA (384 threads):
-//   warp 0      TMA producer (own A rows + own half of W; bytes counted on the LEADER's barrier)
+//   warp 0      TMA producer (own A rows + own half of W; bytes counted on the LEADER's barrier).  Measured and
+//               dropped (round 2): cp.async.bulk.prefetch.tensor of the A boxes 8 k-blocks ahead of the ring, to turn
+//               fc2's HBM-streamed A operand into L2 hits -- fc2 732 -> 779 us at whisper medium, 64 segments (every
+//               pair working on the same rows issues the same prefetches), all GEMMs 2-6 % slower with it everywhere.
 //   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts "stage free" and
 //               "accumulator ready" to both CTAs
 //   warp 2      TMEM allocator (2 x BN columns: the epilogue of tile i overlaps tile i+1's MMAs)
