@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_encoder.py -m gpu -q -x --timeout 600 2>&1 | tail -2
-for pf in 0 default 1; do
-  if [ $pf = default ]; then unset WB_GEMM_A_PREFETCH; else export WB_GEMM_A_PREFETCH=$pf; fi
-  timeout 600 python bench.py --no-cpu-baseline --no-decoder --no-base --sustain-s 0 --steps 5 > gpurun_out/bench_pf_$pf.json 2> gpurun_out/bench_pf_$pf.err; echo "== prefetch $pf exit $?"; python tools/bench_brief.py gpurun_out/bench_pf_$pf.json | sed -n 2,5p
-done
+python tools/prof_encode.py medium 64 > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"gemm2|attention" -s 7 -c 5 -o gpurun_out/prof_medium64_layer -f \
+    python tools/prof_encode.py medium 64 > gpurun_out/ncu_medium64.log 2>&1
+echo "ncu layer exit $?"
+ls -la gpurun_out/prof_medium64_layer.ncu-rep
