@@ -302,7 +302,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     // with the previous steps' offset, the row max computed beside them and used only to decide whether the step must
     // be redone -- takes the max off the dependency chain but holds both P halves in registers (115 -> 164): 485 -> 468
     // TFLOP/s at whisper medium, 64 segments; with 7 of 16 pairs on the FMA pipe as well 445; 7 of 16 without
-    // speculation 494, i.e. flat.)
+    // speculation 494, i.e. flat.  Also round 2: P in its OWN TMEM columns (S0 | S1 | P | O = 240 columns, K ring of
+    // three stages) so that S_{j+2} is issued as soon as S_j has been read instead of after P_j.V_j -- ncu attributes
+    // 17 % of the softmax warps' samples to the "S ready" barrier -- costs an extra barrier round trip per step in both
+    // the softmax and the MMA warp and 11 registers: 476 -> 436 TFLOP/s.)
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int sb = j & 1;
