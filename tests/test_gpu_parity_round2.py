@@ -357,3 +357,35 @@ def test_decoder_bit_reproducible(pkg, model_path):
             assert np.array_equal(lg, ref_logits), rep
             assert np.array_equal(toks, ref_greedy[0]) and np.array_equal(marg, ref_greedy[1]) and np.array_equal(lens, ref_greedy[2]), rep
     ctx.close()
+
+
+def test_decoder_layernorm_fold_rows_with_large_mean(pkg, pyoracle, tmp_path):
+    """The decoder's folded LayerNorms on rows of mean ~50 and spread ~0.03 (decoder positional embedding + 50, small
+    token embedding): the single-token step keeps an F16 copy of x - centre and exact fixed-point statistics of it, so
+    the logits still match the oracle's f64 LayerNorm (rounding x itself to F16 -- ulp 0.03 at 50 -- would not)."""
+    from whisper_rs_b200 import api
+    hp = pkg.ggml_file.ARCHS["tiny"]
+    t = {}
+    for name, a in pkg.ggml_file.random_tensors(hp, 78):
+        if name == "decoder.positional_embedding":
+            a = (50.0 + a * 3.0).astype(np.float32)                      # mean 50, spread 0.03
+        elif name.startswith("decoder.blocks.") and (name.endswith("out.weight") or name.endswith("mlp.2.weight")):
+            a = (a.astype(np.float32) * 0.05).astype(a.dtype)             # the blocks keep the rows near mean 50
+        t[name] = a
+    path = str(tmp_path / "ggml-tiny-dec-mean50.bin")
+    pkg.ggml_file.write_model(path, hp, 0, tensors=t)
+    pcm = pkg.synth.make_segment(6)
+    orc = pyoracle.Oracle(path)
+    orc.pcm_to_mel(pcm)
+    orc.encode(0)
+    ctx = api.WhisperContext.new(path, max_segments=2, max_clips=2)
+    api.whisper_pcm_to_mel(ctx, np.stack([pcm, pcm]))
+    api.whisper_encode(ctx, 1, [0, 0], clip_ids=[0, 1])
+    seq = np.array([ctx.token_sot, 17, 900, 3, 64, 511, 5, 2048], dtype=np.int32)
+    for p in range(len(seq)):                                             # single-token steps: the folded path
+        api.whisper_decode(ctx, np.array([[seq[p]], [seq[p]]], dtype=np.int32), p)
+        ref = orc.decode(seq[p:p + 1], p)
+        got = ctx.logits(1)
+        assert np.isfinite(got).all()
+        assert rel_l2(got, ref) < LOGIT_TOL, (p, rel_l2(got, ref))
+    ctx.close()

@@ -66,14 +66,16 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int n_warps) {
 
 // ---------------------------------------------------------------------------------------------
 // D1: x[s][i][:] = d_te[tok[s][i]][:] + d_pe[n_past + i][:]
-// With `stats` (the LayerNorm-folded single-token step): also leaves the row's (sum, sum of squares) in
-// stats[row] -- the statistics of layer 0's attn_ln -- and an F16 copy of the row, and block 0 clears this
+// With `stats` (the LayerNorm-folded single-token step): also leaves the row's exact mean in center[row], the (sum,
+// sum of squares) of x - center in stats[row] -- the statistics of layer 0's attn_ln -- and an F16 copy of
+// x - center (as in the encoder, gemm2.cu: rounding x itself to F16 would lose the deviations of a row whose mean is
+// large against its spread; the producers downstream keep using, and the consumers keep advancing, that centre), and block 0 clears this
 // launch's rows of the other `n_clear_slots` statistics slots of the step (their producers accumulate with
 // atomics; another sequence group's rows of the same slots may be in use on another stream).
 __global__ void __launch_bounds__(128)
 embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens,
              int n_tok, const int* __restrict__ n_past_p, int d, float* __restrict__ x, DecLnStat* __restrict__ stats,
-             __half* __restrict__ x16, int n_clear_slots) {
+             __half* __restrict__ x16, int n_clear_slots, float* __restrict__ center) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
   __shared__ float red[2][4];
@@ -84,16 +86,36 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
   const __half* e = te + (size_t)tok * d;
   const float* p = pe + (size_t)pos * d;
   float s1 = 0.0f, s2 = 0.0f;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    const float v = __half2float(e[c]) + p[c];
-    x[(size_t)row * d + c] = v;
-    if (stats) {
-      x16[(size_t)row * d + c] = __float2half_rn(v);
-      s1 += v;
-      s2 = fmaf(v, v, s2);
+  constexpr int EMB_MAX = 10;   // d <= 1280 on 128 threads
+  float vals[EMB_MAX];
+#pragma unroll
+  for (int u = 0; u < EMB_MAX; ++u) {
+    const int c = threadIdx.x + u * 128;
+    vals[u] = 0.0f;
+    if (c < d) {
+      vals[u] = __half2float(e[c]) + p[c];
+      x[(size_t)row * d + c] = vals[u];
+      s1 += vals[u];
     }
   }
   if (stats) {
+    __shared__ float red_m[4];
+    s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) red_m[threadIdx.x >> 5] = s1;
+    __syncthreads();
+    const float mean = ((red_m[0] + red_m[1]) + (red_m[2] + red_m[3])) / (float)d;
+    if (threadIdx.x == 0) center[row] = mean;
+    s1 = 0.0f;
+#pragma unroll
+    for (int u = 0; u < EMB_MAX; ++u) {
+      const int c = threadIdx.x + u * 128;
+      if (c < d) {
+        const float w = vals[u] - mean;
+        x16[(size_t)row * d + c] = __float2half_rn(w);
+        s1 += w;
+        s2 = fmaf(w, w, s2);
+      }
+    }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if ((threadIdx.x & 31) == 0) {
@@ -537,6 +559,8 @@ decode_linear_kernel(const DecodeLinear a) {
   // residual row segment and row statistics: requested now, used after the MMAs
   float4 e_res = make_float4(0.f, 0.f, 0.f, 0.f);
   DecLnStat e_st{0ull, 0ull};
+  float e_center = 0.0f;   // producer: the row's centre (x16 copy and statistics are of x - centre)
+  if (a.ln_out && er < a.R) e_center = a.ln_center[er];
   if (a.residual && er < a.R && evec && (a.res_ld & 3) == 0)
     e_res = *reinterpret_cast<const float4*>(a.residual + (size_t)er * a.res_ld + n0 + ef0);
   if (a.ln_in) {   // the row's sub-slots, added as integers (any order gives the same sum)
@@ -623,6 +647,8 @@ decode_linear_kernel(const DecodeLinear a) {
     const double ex2 = (double)(long long)e_st.s2 * (1.0 / (double)DEC_LN_S2_SCALE) * (double)a.ln_inv_d;
     ln_rstd = rsqrtf((float)fmax(ex2 - mu * mu, 0.0) + a.ln_eps);
     ln_nmr = -(float)mu * ln_rstd;
+    // mu is the mean of x - centre: the CTA of the first 16 features moves the centre on for the next producer
+    if (blockIdx.x == 0 && (tid & 3) == 0 && r < a.R) a.ln_center[r] += (float)mu;
   }
   if (evec && (!a.residual || (a.res_ld & 3) == 0)) {   // whole 4-feature group inside N: the prefetched constants
     const float bb[4] = {e_bias.x, e_bias.y, e_bias.z, e_bias.w}, c1[4] = {e_c1.x, e_c1.y, e_c1.z, e_c1.w};
@@ -682,11 +708,13 @@ decode_linear_kernel(const DecodeLinear a) {
   if (a.ln_out) {   // producer of the next folded LayerNorm: row statistics of the f32 result + its F16 copy
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      v[i] -= e_center;   // (the f32 result itself was stored above)
       if (n0 + f0 + i < a.N) {
         s1 += v[i];
         s2 = fmaf(v[i], v[i], s2);
       }
+    }
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
     s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
@@ -801,10 +829,11 @@ __global__ void advance_kernel(int* n_past, int add, int* step) {
 
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
                          const int* n_past_dev, int d, float* x, cudaStream_t st, DecLnStat* stats, __half* x16,
-                         int n_clear_slots) {
-  if (stats && n_seq * n_tok > DEC_LN_ROWS) return cudaErrorInvalidValue;
+                         int n_clear_slots, float* center) {
+  if (stats && (n_seq * n_tok > DEC_LN_ROWS || !center)) return cudaErrorInvalidValue;
+  if (d > 1280) return cudaErrorInvalidValue;
   return launch_pdl(embed_kernel, dim3(n_seq * n_tok), dim3(128), 0, st, te, pe, tokens, n_tok, n_past_dev, d, x, stats,
-                    x16, n_clear_slots);
+                    x16, n_clear_slots, center);
 }
 
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,

@@ -171,6 +171,7 @@ struct wb_ctx {
   int* d_split_cnt = nullptr;                    // per (row, head) arrival counter of the split cross-attention
   int dec_n_seq = 0;
   const float *d_ones = nullptr, *d_zeros = nullptr;   // identity affine for the prompt pass's plain LayerNorm
+  float* dec_ln_center = nullptr;                // [DEC_LN_ROWS] per-row centre of the folded decode step
   wb::DecLnStat* dec_ln_stats = nullptr;         // [3 Lt + 1][DEC_LN_SUB][DEC_LN_ROWS] row statistics of the folded single-token step
   cudaGraphExec_t step_graph = nullptr;          // one single-token greedy step, captured per n_seq
   int step_graph_n_seq = 0, step_graph_max_new = 0, step_graph_eot = -1;

@@ -82,6 +82,7 @@ static int run_linear_rows(wb_ctx* ctx, const Linear& l, const __half* x, const 
   a.out_f16 = epi.out_f16;
   a.out_ld = epi.out_ld;
   a.top2 = top2;
+  a.ln_center = epi.ln_center;
   if (epi.ln_stats_in) {   // folded LayerNorm, consumer side: l carries gamma (upload_cat_ln)
     a.ln_in = epi.ln_stats_in;
     a.ln_c1 = l.ln_c1;
@@ -169,6 +170,7 @@ int decode_setup(wb_ctx* ctx, const ModelFileView& mv) {
     if ((rc = upload_f32_vec(ctx, zeros, &ctx->d_zeros))) return rc;
   }
   if ((rc = dev_alloc(ctx, &ctx->dec_ln_stats, (size_t)DEC_LN_SLOT * (3 * Lt + 1)))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->dec_ln_center, (size_t)DEC_LN_ROWS))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_npast, 4))) return rc;
   ctx->d_step = ctx->d_npast + 1;
   // split-K cross-attention partials (only used for few rows: n_tok <= 8)
@@ -229,7 +231,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
   {
     LaunchTimer t(ctx, "dec_embed");
     WB_CK(launch_embed(ctx->d_te, ctx->d_pe, tokens_dev, n_seq, n_tok, ctx->d_npast, d, dx, st,
-                       fold ? slot(0) : nullptr, d_ln, fold ? 3 * Lt : 0));
+                       fold ? slot(0) : nullptr, d_ln, fold ? 3 * Lt : 0, fold ? ctx->dec_ln_center + r0 : nullptr));
   }
   const int n_split = n_tok <= 8 ? decode_cross_splits(n_seq, H, T, ctx->num_sms) : 1;
   for (int il = 0; il < Lt; ++il) {
@@ -243,7 +245,10 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out = d_qkv;
       e.out_f16 = 1;
       e.out_ld = 3 * d;
-      if (fold) e.ln_stats_in = slot(3 * il);
+      if (fold) {
+        e.ln_stats_in = slot(3 * il);
+        e.ln_center = ctx->dec_ln_center + r0;
+      }
       if (!skip_lin && (rc = run_linear_rows(ctx, l.qkv, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!skip_self) {
@@ -261,6 +266,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out_ld = d;
       if (fold) {
         e.ln_stats_out = slot(3 * il + 1);
+        e.ln_center = ctx->dec_ln_center + r0;
         e.x16_out = d_ln;
         e.x16_ld = d;
       }
@@ -275,7 +281,10 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out = d_q;
       e.out_f16 = 1;
       e.out_ld = d;
-      if (fold) e.ln_stats_in = slot(3 * il + 1);
+      if (fold) {
+        e.ln_stats_in = slot(3 * il + 1);
+        e.ln_center = ctx->dec_ln_center + r0;
+      }
       if (!skip_lin && (rc = run_linear_rows(ctx, l.cq, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     if (!skip_cross) {
@@ -297,6 +306,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out_ld = d;
       if (fold) {
         e.ln_stats_out = slot(3 * il + 2);
+        e.ln_center = ctx->dec_ln_center + r0;
         e.x16_out = d_ln;
         e.x16_ld = d;
       }
@@ -312,7 +322,10 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out = d_hid;
       e.out_f16 = 1;
       e.out_ld = 4 * d;
-      if (fold) e.ln_stats_in = slot(3 * il + 2);
+      if (fold) {
+        e.ln_stats_in = slot(3 * il + 2);
+        e.ln_center = ctx->dec_ln_center + r0;
+      }
       if (!skip_lin && (rc = run_linear_rows(ctx, l.fc1, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
     {
@@ -324,6 +337,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       e.out_ld = d;
       if (fold && il + 1 < Lt) {   // (decoder.ln in front of the logits keeps its kernel: d_te is shared with the embedding)
         e.ln_stats_out = slot(3 * il + 3);
+        e.ln_center = ctx->dec_ln_center + r0;
         e.x16_out = d_ln;
         e.x16_ld = d;
       }

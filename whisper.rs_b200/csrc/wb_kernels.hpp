@@ -182,7 +182,7 @@ cudaError_t launch_abs_sum_f16(const __half* x, int rows, int cols, long long ro
 // D1: x[s][i][:] = d_te[tok] + d_pe[n_past + i]
 cudaError_t launch_embed(const __half* te, const float* pe, const int* tokens, int n_seq, int n_tok,
                          const int* n_past_dev, int d, float* x, cudaStream_t st, DecLnStat* stats = nullptr,
-                         __half* x16 = nullptr, int n_clear_slots = 0);
+                         __half* x16 = nullptr, int n_clear_slots = 0, float* center = nullptr);
 // D2: append this step's K/V to the F16 cache [seq][n_text_ctx][d], causal attention over it
 cudaError_t launch_decode_self_attn(const __half* qkv, int d, __half* kc, __half* vc, int n_seq, int n_tok,
                                     const int* n_past_dev, int n_text_ctx, int H, __half* out, cudaStream_t st);
@@ -213,7 +213,8 @@ struct DecodeLinear {
   const DecLnStat* ln_in = nullptr;   // consumer: per-row (sum, sum of squares) of x (fixed point); w carries gamma, bias = c2
   const float* ln_c1 = nullptr;    //           c1[n] = sum_k w[n][k]
   float ln_inv_d = 0.0f, ln_eps = 1e-5f;
-  DecLnStat* ln_out = nullptr;     // producer: statistics of the f32 result rows, accumulated with integer atomics
+  DecLnStat* ln_out = nullptr;     // producer: statistics of (result - centre) per row, accumulated with integer atomics
+  float* ln_center = nullptr;      // [R] per-row centre: read by producers, advanced by the row mean by consumers (CTA 0)
   __half* x16_out = nullptr;       //           and their F16 copy [R][x16_ld] (the next linear's activations)
   int x16_ld = 0;
 };
