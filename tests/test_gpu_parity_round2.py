@@ -389,3 +389,34 @@ def test_decoder_layernorm_fold_rows_with_large_mean(pkg, pyoracle, tmp_path):
         assert np.isfinite(got).all()
         assert rel_l2(got, ref) < LOGIT_TOL, (p, rel_l2(got, ref))
     ctx.close()
+
+
+def test_encode_graph_cache_over_alternating_shapes(pkg, pyoracle, model_path):
+    """wb_encode replays a captured CUDA graph per shape (n_seg, audio context, mel length); alternating between shapes
+    -- full batches and a ragged tail, two audio contexts, two clip lengths -- must keep returning, bit for bit, what
+    the first (directly launched) call of each shape returned, and the oracle's result."""
+    from whisper_rs_b200 import api
+    arch = "micro"
+    hp = pkg.ggml_file.ARCHS[arch]
+    n = 2 * hp.n_audio_ctx * 160
+    ctx = api.WhisperContext.new(model_path(arch), max_segments=3, max_clips=3, max_clip_samples=n, decode_capacity=False)
+    clips = np.stack([pkg.synth.make_segment(130 + s, n, 0.1) for s in range(3)])
+    shapes = [(3, 0, n), (1, 0, n), (2, 40, n), (2, 0, n // 2), (3, 24, n)]        # (n_seg, audio ctx, samples): 5 > the cache of 4
+    first = {}
+    launches0 = ctx.timings()["n_kernel_launches"]
+    for rep in range(4):
+        for sh in shapes:
+            n_seg, n_ctx, ns = sh
+            ctx.set_audio_ctx(n_ctx)
+            api.whisper_pcm_to_mel(ctx, clips[:, :ns])
+            api.whisper_encode(ctx, 1, [0] * n_seg, clip_ids=list(range(n_seg)))
+            got = np.stack([ctx.encoder_out(s) for s in range(n_seg)])
+            if rep == 0:
+                first[sh] = got
+            else:
+                assert np.array_equal(got, first[sh]), (rep, sh)
+    assert ctx.timings()["n_kernel_launches"] > launches0
+    orc = pyoracle.Oracle(model_path(arch))
+    orc.pcm_to_mel(clips[1])
+    assert rel_l2(first[(3, 0, n)][1], orc.encode(0)) < ENC_TOL
+    ctx.close()

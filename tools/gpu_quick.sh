@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_pipeline.py tests/test_gpu_cabi.py -m gpu -q -x --timeout 600 2>&1 | tail -3
-timeout 900 python -m pytest tests/test_gpu_parity_round2.py -m gpu -q -x --timeout 600 -k "decoder or small_full or greedy_after or writes_outside" 2>&1 | tail -3
-for a in "small 32" "large-v3 15"; do timeout 300 python tools/dec_groups.py $a 224 2>&1 | tail -1; done
+timeout 900 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_pipeline.py -m gpu -q -x --timeout 600 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_parity_round2.py -m gpu -q -x --timeout 600 -k "graph_cache or base_batch16 or writes_outside or audio_ctx" 2>&1 | tail -3

@@ -752,7 +752,9 @@ void wb_ctx_free(wb_ctx* ctx) {
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   ctx->free_events.clear();
   if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
-  if (ctx->enc_graph.exec) cudaGraphExecDestroy(ctx->enc_graph.exec);
+  for (auto& g : ctx->enc_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->enc_graphs.clear();
   for (int g = 0; g < WB_MAX_DEC_GROUPS; ++g) {
     if (ctx->dec_group_stream[g]) cudaStreamDestroy(ctx->dec_group_stream[g]);
     if (ctx->dec_group_done[g]) cudaEventDestroy(ctx->dec_group_done[g]);
@@ -1278,21 +1280,26 @@ int wb_encode(wb_ctx* ctx, const int32_t* clip_ids, const size_t* mel_offsets, i
   // Not used with per-kernel timing or checkpoints (both add launches that depend on the mode).  WB_ENC_GRAPH=0: off.
   static const bool graph_off = [] { const char* e = getenv("WB_ENC_GRAPH"); return e && e[0] == '0'; }();
   if (!graph_off && !ctx->time_kernels && !chk) {
-    wb::EncodeGraph& eg = ctx->enc_graph;
-    const bool same = eg.n_seg == n_seg && eg.T == T && eg.mel_n_len == ctx->mel_n_len && eg.norm_mode == norm_mode;
-    if (!same) {
+    // a few shapes are kept (a long clip runs full batches and one ragged tail; a server alternates batch sizes)
+    wb::EncodeGraph* found = nullptr;
+    for (auto& g : ctx->enc_graphs)
+      if (g.n_seg == n_seg && g.T == T && g.mel_n_len == ctx->mel_n_len && g.norm_mode == norm_mode) found = &g;
+    if (!found) {
       // first call of a shape: run directly (each kernel instantiation opts in to its shared-memory size at its first
       // launch -- not something to do inside a capture); the next call of the same shape captures
-      if (eg.exec) {
-        cudaGraphExecDestroy(eg.exec);
-        eg.exec = nullptr;
+      if (ctx->enc_graphs.size() >= WB_MAX_ENC_GRAPHS) {   // forget the oldest shape
+        if (ctx->enc_graphs.front().exec) cudaGraphExecDestroy(ctx->enc_graphs.front().exec);
+        ctx->enc_graphs.erase(ctx->enc_graphs.begin());
       }
-      eg.n_seg = n_seg;
-      eg.T = T;
-      eg.mel_n_len = ctx->mel_n_len;
-      eg.norm_mode = norm_mode;
+      wb::EncodeGraph g;
+      g.n_seg = n_seg;
+      g.T = T;
+      g.mel_n_len = ctx->mel_n_len;
+      g.norm_mode = norm_mode;
+      ctx->enc_graphs.push_back(g);
       if ((rc = encode_launches())) return rc;
     } else {
+    wb::EncodeGraph& eg = *found;
     if (!eg.exec) {
       const int64_t l0 = ctx->tm.n_kernel_launches;
       cudaGraph_t graph = nullptr;

@@ -68,6 +68,7 @@ struct KernelClock {   // device time per kernel family (CUDA events on the hand
 
 constexpr int WB_N_TICKETS = 8;
 constexpr int WB_MAX_DEC_GROUPS = 4;
+constexpr size_t WB_MAX_ENC_GRAPHS = 4;
 
 struct wb_ctx {
   wb_config cfg{};
@@ -145,7 +146,7 @@ struct wb_ctx {
   size_t cross_slab = 0;              // elements per slab = max_segments * T * d
   int Tp = 0;
   wb::EncodeMaps enc_maps;
-  wb::EncodeGraph enc_graph;
+  std::vector<wb::EncodeGraph> enc_graphs;   // captured encodes, one per shape seen twice (at most WB_MAX_ENC_GRAPHS)
   int enc_n_seg = 0;                  // segments of the last wb_encode
   int exp_n_audio_ctx = 0;            // exp_n_audio_ctx (src/main.rs:362): > 0 shortens the encoder's audio context
   int enc_T = 0;                      // audio context the last wb_encode ran with (rows per segment of its outputs)
