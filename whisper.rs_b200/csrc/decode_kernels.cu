@@ -251,7 +251,11 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
 // finishes last merges them.
 constexpr int CROSS_THREADS = 256;
 constexpr int CROSS_MAX_SPAN = 1536;
-constexpr int CROSS_U = 4;          // K rows AND V rows per lane requested together (8 x 16 bytes in flight per lane)
+// CROSS_U (template parameter) = K rows AND V rows per lane requested together (2 U x 16 bytes in flight per lane);
+// MINB = CTAs per SM the register budget is held to.  <4, 3> keeps 8 loads per lane in flight on 444 CTA slots;
+// <3, 4> trades two of them for 592 slots.  The kernel is bound by the bytes a CTA keeps in flight, so the launch
+// picks the variant that holds every (head, sequence) item in ONE wave: whisper medium with 32 sequences has 512
+// items -- 2.03 ms per step on 444 slots (a second wave of 68 CTAs), 1.81 ms on 592 (round 2, tools/dec_groups.py).
 constexpr int CROSS_GROUPS = (CROSS_THREADS / 32) * 4;   // 8-lane groups per CTA: one key row each per instruction
 
 // One pass over the keys (online softmax): every 8-lane group walks its rows with K and V requested together
@@ -259,7 +263,8 @@ constexpr int CROSS_GROUPS = (CROSS_THREADS / 32) * 4;   // 8-lane groups per CT
 // Against two passes (scores -> shared memory, block softmax, then V) there is no mid-kernel barrier during
 // which all resident CTAs stop streaming at the same time, and twice the loads are in flight in steady state.
 // The probabilities are rounded to F16 before P.V as in the reference, relative to the running maximum.
-__global__ void __launch_bounds__(CROSS_THREADS, 3)
+template <int CROSS_U, int MINB>
+__global__ void __launch_bounds__(CROSS_THREADS, MINB)
 decode_cross_attn_kernel(const __half* __restrict__ q, int d, const __half* __restrict__ k, const __half* __restrict__ v,
                          long long ld, long long head_stride, int n_tok, int T, int span, __half* __restrict__ out,
                          float* __restrict__ part_o, float* __restrict__ part_ml, int n_split, int* __restrict__ split_cnt) {
@@ -857,7 +862,12 @@ cudaError_t launch_decode_cross_attn(const __half* q, int d, const __half* k, co
                                      float* part_o, float* part_ml, int n_split, int* split_cnt, cudaStream_t st) {
   const int span = (T + n_split - 1) / n_split;
   if (span > CROSS_MAX_SPAN) return cudaErrorInvalidValue;
-  return launch_pdl(decode_cross_attn_kernel, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
+  // one wave if possible: 3 CTAs per SM with the deeper load queue, else 4 per SM
+  const int n_ctas = H * n_seq * n_split;
+  if (n_ctas <= 3 * 148 || n_ctas > 4 * 148)
+    return launch_pdl(decode_cross_attn_kernel<4, 3>, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
+                      head_stride, n_tok, T, span, out, part_o, part_ml, n_split, split_cnt);
+  return launch_pdl(decode_cross_attn_kernel<3, 4>, dim3(H, n_seq, n_split), dim3(CROSS_THREADS), 0, st, q, d, k, v, ld_kv,
                     head_stride, n_tok, T, span, out, part_o, part_ml, n_split, split_cnt);
 }
 
