@@ -508,7 +508,10 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 // of one per loop iteration (the step is a chain of ~100 such latency-bound kernels).
 constexpr int DL_ROWS = 16;       // weight rows (output features) per CTA
 
-template <int U, int NW>
+// PIPE (K longer than one round of 32 U NW, few CTAs: fc2): the next round's weights are requested before the current
+// round's MMAs, in a second set of registers, so a CTA's rounds overlap instead of each paying a full HBM / L2 round
+// trip (4 rounds at d = 1024 / 1280).  Costs ~2 U x 4 registers per thread: only for launches of at most one CTA per SM.
+template <int U, int NW, bool PIPE = false>
 __global__ void __launch_bounds__(32 * NW)
 decode_linear_kernel(const DecodeLinear a) {
   constexpr int DL_THREADS = 32 * NW;
@@ -591,6 +594,44 @@ decode_linear_kernel(const DecodeLinear a) {
         mma_16816(acc[j], A0[u].z, B0[u].z, A0[u].w, B0[u].w, X[u][j].z, X[u][j].w);
       }
     k += 32 * U;
+  }
+  if (PIPE && pre) {
+    // rounds 1, 2, ...: ping-pong between two register sets, the request for round i + 1 issued before round i's MMAs
+    uint4 A1[U], B1[U];
+    auto request = [&](uint4 (&A)[U], uint4 (&B)[U], int kk) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        A[u] = ld_nc_v4(wa + kk + 32 * u);
+        B[u] = ld_nc_v4(wb + kk + 32 * u);
+      }
+    };
+    auto consume = [&](const uint4 (&A)[U], const uint4 (&B)[U], int kk) {
+      uint4 X[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[u][j] = *reinterpret_cast<const uint4*>(xg + (size_t)(8 * j) * a.ldx + kk + 32 * u);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mma_16816(acc[j], A[u].x, B[u].x, A[u].y, B[u].y, X[u][j].x, X[u][j].y);
+          mma_16816(acc[j], A[u].z, B[u].z, A[u].w, B[u].w, X[u][j].z, X[u][j].w);
+        }
+    };
+    bool have1 = k + 32 * U <= k_hi;
+    if (have1) request(A1, B1, k);
+    while (have1) {
+      const bool have0 = k + 64 * U <= k_hi;
+      if (have0) request(A0, B0, k + 32 * U);
+      consume(A1, B1, k);
+      k += 32 * U;
+      if (!have0) break;
+      have1 = k + 64 * U <= k_hi;
+      if (have1) request(A1, B1, k + 32 * U);
+      consume(A0, B0, k);
+      k += 32 * U;
+    }
   }
   for (; k + 32 * U <= k_hi; k += 32 * U) {
     uint4 A[U], B[U], X[U][4];
@@ -882,8 +923,17 @@ cudaError_t launch_argmax(const float* logits, int n_seq, int n_vocab, int* next
 cudaError_t launch_decode_linear(const DecodeLinear& a, cudaStream_t st) {
   if (a.R < 1 || a.R > 32 || a.N < 1 || a.K % 64 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
   const dim3 grid((a.N + DL_ROWS - 1) / DL_ROWS);
-#define WB_DL(U, NW) \
-  if (a.K % (32 * (U) * (NW)) == 0 || ((U) == 4 && (NW) == 4)) return launch_pdl(decode_linear_kernel<U, NW>, grid, dim3(32 * (NW)), 0, st, a)
+  // more than one round per CTA and few CTAs (fc2: N = d): the software-pipelined variant.  Its ~170-230 registers per
+  // thread keep the NEXT kernel's CTAs (resident early through programmatic dependent launch, to pull their weights)
+  // off the SMs it runs on, so it pays while it occupies less than half of them: small (48 CTAs) 0.767 -> 0.728 ms per
+  // step, medium (64) 1.81 -> 1.74, large-v3 (80) 2.14 -> 2.20 (measured, tools/dec_groups.py) -- hence the bound
+  const bool pipe = (int)grid.x <= 64;
+#define WB_DL(U, NW)                                                                                                  \
+  if (a.K % (32 * (U) * (NW)) == 0 || ((U) == 4 && (NW) == 4)) {                                                       \
+    if (pipe && a.K >= 2 * 32 * (U) * (NW) && (NW) == 8)                                                               \
+      return launch_pdl(decode_linear_kernel<U, NW, true>, grid, dim3(32 * (NW)), 0, st, a);                           \
+    return launch_pdl(decode_linear_kernel<U, NW>, grid, dim3(32 * (NW)), 0, st, a);                                   \
+  }
   // many CTAs (the vocabulary projection: 3242 of them): waves x per-CTA latency sets the time, so the variant
   // with the fewest registers (most resident CTAs) wins over the one with every load in flight
   if ((int)grid.x > 16 * 148 && a.K % 256 == 0) WB_DL(2, 4);
