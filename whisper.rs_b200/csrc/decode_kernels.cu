@@ -143,16 +143,22 @@ embed_kernel(const __half* __restrict__ te, const float* __restrict__ pe, const 
 // second operand when the first (V) is F16.
 constexpr int SELF_THREADS = 128;
 constexpr int SELF_MAX_CTX = 448 + 64;
-constexpr int SELF_U = 8;          // key / value rows per lane requested before the first is used
+constexpr int SELF_U = 4;          // key rows AND value rows per lane requested together
+constexpr int SELF_GROUPS = (SELF_THREADS / 32) * 4;   // 8-lane groups per CTA: one cache row each per instruction
 
+// One pass over the cached keys (online softmax, K and V rows requested together, as decode_cross_attn_kernel):
+// round 1 ran scores -> shared memory -> block softmax -> P.V, i.e. two dependent L2 round trips and six block
+// barriers per token for a few hundred keys; here every 8-lane group keeps a running (max, denominator, 8 output
+// dims per lane) over its rows and the 16 groups are merged once.  The probabilities are rounded to F16 before P.V
+// relative to the running maximum (the reference rounds the normalised ones: the same F16 grid up to a power of two
+// when the maximum is final, within the logit tolerance otherwise).
 __global__ void __launch_bounds__(SELF_THREADS)
 decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restrict__ kc, __half* __restrict__ vc,
                         int n_tok, const int* __restrict__ n_past_p, int n_text_ctx, __half* __restrict__ out) {
   pdl_launch_dependents();   // the next kernel of the step may become resident now; it blocks at its own wait
   pdl_wait();                // everything this kernel reads is the previous kernels' output
-  __shared__ float sc[SELF_MAX_CTX];
-  __shared__ float red[SELF_THREADS / 32];
-  __shared__ float opart[SELF_THREADS / 32][4][DH];
+  __shared__ float g_m[SELF_GROUPS], g_l[SELF_GROUPS];
+  __shared__ float g_o[SELF_GROUPS][DH];
   const int h = blockIdx.x, s = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_past = *n_past_p;
@@ -166,23 +172,32 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
     *reinterpret_cast<uint4*>(vbase + (size_t)(n_past + i) * d + ch * 8) = *reinterpret_cast<const uint4*>(src + 2 * d);
   }
   __syncthreads();
-  const int sub = lane >> 3, ch = lane & 7;   // 4 keys per warp instruction, 8 lanes per key row
+  const int sub = lane >> 3, ch = lane & 7;   // 4 rows per warp instruction, 8 lanes per 128-byte row
+  constexpr int RPI = SELF_GROUPS;            // rows per CTA iteration
   for (int i = 0; i < n_tok; ++i) {
     const int Tk = n_past + i + 1;            // causal: keys 0 .. n_past + i
     float q[8];
     unpack8(*reinterpret_cast<const uint4*>(qkv + (size_t)(s * n_tok + i) * 3 * d + h * DH + ch * 8), q);
-    // SELF_U key rows per lane in flight (the loop is pure L2 / HBM latency otherwise)
-    constexpr int STRIDE = (SELF_THREADS / 32) * 4;
-    for (int t0 = warp * 4; t0 < Tk; t0 += STRIDE * SELF_U) {
-      uint4 kv[SELF_U];
+    float m = -INFINITY, l = 0.0f, o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int t0 = warp * 4; t0 < Tk; t0 += SELF_U * RPI) {
+      uint4 kv[SELF_U], vv[SELF_U];
 #pragma unroll
       for (int u = 0; u < SELF_U; ++u) {
-        const int t = t0 + u * STRIDE + sub;
+        const int t = t0 + u * RPI + sub;
         kv[u] = t < Tk ? *reinterpret_cast<const uint4*>(kbase + (size_t)t * d + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < SELF_U; ++u) {
-        const int t = t0 + u * STRIDE + sub;
+        const int t = t0 + u * RPI + sub;
+        vv[u] = t < Tk ? *reinterpret_cast<const uint4*>(vbase + (size_t)t * d + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float sc[SELF_U];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < SELF_U; ++u) {
+        const int t = t0 + u * RPI + sub;
         float kf[8];
         unpack8(kv[u], kf);
         float acc = 0.0f;
@@ -191,51 +206,48 @@ decode_self_attn_kernel(const __half* __restrict__ qkv, int d, __half* __restric
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ch == 0 && t < Tk) sc[t] = acc;
+        sc[u] = t < Tk ? acc : -INFINITY;
+        bm = fmaxf(bm, sc[u]);
+      }
+      const float m_new = fmaxf(m, bm);
+      if (m_new > -INFINITY) {   // (group-uniform: the 8 lanes hold the same scores)
+        const float alpha = __expf(m - m_new);   // 0 on the group's first rows (m = -inf)
+        l *= alpha;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= alpha;
+#pragma unroll
+        for (int u = 0; u < SELF_U; ++u) {
+          const float e = __expf(sc[u] - m_new);   // 0 for a row past the end
+          l += e;
+          const float p = __half2float(__float2half_rn(e));   // P -> F16 before P.V
+          float vf[8];
+          unpack8(vv[u], vf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
+        }
+        m = m_new;
       }
     }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int t = tid; t < Tk; t += SELF_THREADS) mx = fmaxf(mx, sc[t]);
-    mx = block_max(mx, red, SELF_THREADS / 32);
-    float sum = 0.0f;
-    for (int t = tid; t < Tk; t += SELF_THREADS) {
-      const float e = __expf(sc[t] - mx);
-      sc[t] = e;
-      sum += e;
-    }
-    sum = block_sum(sum, red, SELF_THREADS / 32);
-    const float inv = 1.0f / sum;
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < Tk; t0 += STRIDE * SELF_U) {
-      uint4 vv[SELF_U];
-#pragma unroll
-      for (int u = 0; u < SELF_U; ++u) {
-        const int t = t0 + u * STRIDE + sub;
-        vv[u] = t < Tk ? *reinterpret_cast<const uint4*>(vbase + (size_t)t * d + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < SELF_U; ++u) {
-        const int t = t0 + u * STRIDE + sub;
-        const float p = t < Tk ? __half2float(__float2half_rn(sc[t] * inv)) : 0.0f;
-        float vf[8];
-        unpack8(vv[u], vf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(p, vf[j], o[j]);
-      }
+    const int grp = warp * 4 + sub;
+    if (ch == 0) {
+      g_m[grp] = m;
+      g_l[grp] = l;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) opart[warp][sub][ch * 8 + j] = o[j];
+    for (int j = 0; j < 8; ++j) g_o[grp][ch * 8 + j] = o[j];
     __syncthreads();
     if (tid < DH) {
-      float r = 0.0f;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < SELF_THREADS / 32; ++w)
+      for (int gq = 0; gq < SELF_GROUPS; ++gq) mx = fmaxf(mx, g_m[gq]);
+      float sum = 0.0f, r = 0.0f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) r += opart[w][u][tid];
-      out[(size_t)(s * n_tok + i) * d + h * DH + tid] = __float2half_rn(r);
+      for (int gq = 0; gq < SELF_GROUPS; ++gq) {
+        const float w = g_m[gq] > -INFINITY ? __expf(g_m[gq] - mx) : 0.0f;
+        sum = fmaf(w, g_l[gq], sum);
+        r = fmaf(w, g_o[gq][tid], r);
+      }
+      out[(size_t)(s * n_tok + i) * d + h * DH + tid] = __float2half_rn(sum > 0.0f ? r / sum : 0.0f);
     }
     __syncthreads();
   }
