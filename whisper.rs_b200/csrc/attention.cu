@@ -305,7 +305,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qk_map, const __gri
     // speculation 494, i.e. flat.  Also round 2: P in its OWN TMEM columns (S0 | S1 | P | O = 240 columns, K ring of
     // three stages) so that S_{j+2} is issued as soon as S_j has been read instead of after P_j.V_j -- ncu attributes
     // 17 % of the softmax warps' samples to the "S ready" barrier -- costs an extra barrier round trip per step in both
-    // the softmax and the MMA warp and 11 registers: 476 -> 436 TFLOP/s.)
+    // the softmax and the MMA warp and 11 registers: 476 -> 436 TFLOP/s.  Late round 2, all A/B'd against this kernel in
+    // the same gpurun call at whisper medium, 64 segments (profiles/r02_attn_*): THREE CTAs per SM -- one S / P buffer,
+    // the denominator summed in the softmax threads so that S | O fit 128 TMEM columns, 64-key stages in a ring of three,
+    // 112 registers -- makes softmax_j -> P_j V_j -> Q K_{j+1}^T -> softmax_{j+1} one dependent chain per CTA: 480 -> 360.
+    // Probing the next step's "S ready" barrier early with mbarrier.test_wait: 485 -> 468 (on an idle SM a completed
+    // try_wait is only 50 cycles, tools/ubench/mbar_lat.cu: the ~250 cycles a step spends before its TMEM load are the
+    // dependent address / predicate / branch instructions queued behind the other warps, not the barrier).  TWO softmax
+    // warpgroups per tile taking alternate steps (4 softmax warps per scheduler, the row max handed over through shared
+    // memory and named barriers): 471 -> 432 as long as P overwrote S (the warpgroup then idles ~1000 cycles for
+    // P_j V_j -> Q K_{j+2}^T); with P in its own TMEM columns, 64-key K / V^T rings and an "S read" barrier 490 -> 476,
+    // the single MMA warp now the pace-setter (4 waits x ~180 cycles + 8 MMAs + commits = the whole step); with TWO
+    // MMA-issuing warps that also issue their operand's TMA loads (no TMA warp, no "stage free" barriers) the step drops
+    // from ~1330 to ~1200 cycles in the clock trace, but 479 -> 481 TFLOP/s and 698 -> 697 segments/s in the bench: the
+    // chip sits at its 985 W power cap either way (SM clock 1.39 GHz of 1.965), so cycles saved come back as a lower
+    // clock.  The variant is kept as profiles/r02_attn_variant_two_softmax_warpgroups.patch.)
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int sb = j & 1;
