@@ -34,7 +34,8 @@
 // behind the shape (tools/ubench): a tcgen05.mma of M = 128 costs max(~47, N/2) cycles, so the 64-
 // and 80-wide tiles run at the instruction floor; the issuing thread is blocked while its MMA
 // executes; an mbarrier wait costs ~175 cycles even when already complete; FMNMX3 costs the same as
-// FMNMX; ex2.approx.f16x2 gives no MUFU throughput over the f32 form.  Variants measured slower or
+// FMNMX; ex2.approx.f16x2 gives no MUFU throughput over the f32 form (SASS: two MUFU.EX2.F16 plus a PRMT to merge
+// the halves -- five issue slots per key pair against four).  Variants measured slower or
 // equal on B200: 128-key tiles with P handed over in halves, 16 softmax warps with half a row per
 // thread, software-pipelining the next step's TMEM load and max under the exponentials, two
 // warpgroups per CTA with one or two MMA warps (with and without a phase offset).
