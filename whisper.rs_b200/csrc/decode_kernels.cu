@@ -975,6 +975,26 @@ cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int
                     out_margin, out_len, done, max_new, step_dev, eot, n_past_dev, advance_by);
 }
 
+// L2 prefetch of a byte range (4 KB per cp.async.bulk.prefetch): the decoder step issues it on a side branch of the step
+// graph for the NEXT layer's cross K / V while the current layer's latency-bound linears leave HBM idle (an
+// L2::evict_last cache hint on the prefetch changes nothing)
+__global__ void l2_prefetch_kernel(const char* p0, const char* p1, long long n_chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const char* p = i < n_chunks ? p0 + i * 4096 : p1 + (i - n_chunks) * 4096;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(4096) : "memory");
+  }
+}
+
+cudaError_t launch_l2_prefetch(const void* p0, const void* p1, size_t bytes_each, cudaStream_t st) {
+  const long long n_chunks = (long long)(bytes_each / 4096);
+  if (n_chunks <= 0) return cudaSuccess;
+  const int threads = 128;
+  int blocks = (int)((2 * n_chunks + threads - 1) / threads);
+  if (blocks > 32) blocks = 32;
+  l2_prefetch_kernel<<<blocks, threads, 0, st>>>(static_cast<const char*>(p0), static_cast<const char*>(p1), n_chunks);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st) {
   return launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, n_past_dev, add, step_dev);
 }

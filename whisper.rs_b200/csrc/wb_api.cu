@@ -760,6 +760,9 @@ void wb_ctx_free(wb_ctx* ctx) {
     if (ctx->dec_group_done[g]) cudaEventDestroy(ctx->dec_group_done[g]);
   }
   if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
+  if (ctx->dec_pf_stream) cudaStreamDestroy(ctx->dec_pf_stream);
+  if (ctx->dec_pf_fork) cudaEventDestroy(ctx->dec_pf_fork);
+  if (ctx->dec_pf_join) cudaEventDestroy(ctx->dec_pf_join);
   for (void* p : ctx->allocs) cudaFree(p);
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)

@@ -181,6 +181,11 @@ struct wb_ctx {
   cudaStream_t dec_group_stream[WB_MAX_DEC_GROUPS] = {};   // capture-only streams of the branches
   cudaEvent_t dec_group_done[WB_MAX_DEC_GROUPS] = {};
   cudaEvent_t dec_fork = nullptr;
+  // side branch of the step graph that prefetches the next layer's cross K / V into L2 (decode_pass)
+  cudaStream_t dec_pf_stream = nullptr;
+  cudaEvent_t dec_pf_fork = nullptr, dec_pf_join = nullptr;
+  int dec_pf_mb = 0;           // MB per layer (0: off)
+  bool dec_pf_active = false;  // set while the single-token step is being captured
 
   // ---- results read back without blocking (wb_encoder_digest_async / wb_wait)
   cudaEvent_t ev_ticket[WB_N_TICKETS] = {};

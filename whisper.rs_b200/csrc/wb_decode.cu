@@ -234,6 +234,21 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
                        fold ? slot(0) : nullptr, d_ln, fold ? 3 * Lt : 0, fold ? ctx->dec_ln_center + r0 : nullptr));
   }
   const int n_split = n_tok <= 8 ? decode_cross_splits(n_seq, H, T, ctx->num_sms) : 1;
+  // L2 prefetch branch (captured single-token step only): the cross K / V of the first n_pf sequences of layer il
+  const bool prefetch = ctx->dec_pf_active && n_tok == 1 && ctx->dec_pf_mb > 0 && !skip_cross;
+  const size_t seq_kv_bytes = (size_t)T * d * sizeof(__half);
+  int n_pf = prefetch ? (int)(((size_t)ctx->dec_pf_mb << 20) / (2 * seq_kv_bytes)) : 0;
+  if (n_pf > n_seq) n_pf = n_seq;
+  auto prefetch_layer = [&](int il) -> cudaError_t {
+    cudaStream_t ps = ctx->dec_pf_stream;
+    cudaError_t e = cudaEventRecord(ctx->dec_pf_fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, ctx->dec_pf_fork, 0);
+    const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab + (size_t)seq0 * T * d;
+    if (e == cudaSuccess) e = launch_l2_prefetch(kx, kx + ctx->cross_slab, (size_t)n_pf * seq_kv_bytes, ps);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->dec_pf_join, ps);
+    return e;
+  };
+  if (n_pf > 0) WB_CK(prefetch_layer(0));
   for (int il = 0; il < Lt; ++il) {
     const DecLayer& l = ctx->dec[il];
     if (!fold) {   // D2: self-attention
@@ -287,6 +302,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
       }
       if (!skip_lin && (rc = run_linear_rows(ctx, l.cq, d_ln, ctx->m_ln, R, e, "dec_gemm", nullptr, st))) return rc;
     }
+    if (n_pf > 0) WB_CK(cudaStreamWaitEvent(st, ctx->dec_pf_join, 0));   // join: the branch always ends before its consumer
     if (!skip_cross) {
       LaunchTimer t(ctx, "dec_cross_attn");
       const __half* kx = ctx->cross + (size_t)(2 * il) * ctx->cross_slab + (size_t)seq0 * T * d;   // segment seq0 onwards
@@ -297,6 +313,7 @@ static int decode_pass(wb_ctx* ctx, const int* tokens_dev, int n_seq, int n_tok,
                                      ctx->d_part_o + (size_t)seq0 * H * 8 * 64, ctx->d_part_ml + (size_t)seq0 * H * 8 * 2, n_split,
                                      ctx->d_split_cnt + (size_t)seq0 * H, st));
     }
+    if (n_pf > 0 && il + 1 < Lt) WB_CK(prefetch_layer(il + 1));   // behind this layer's cross-attention, under the linears that follow
     {
       GemmEpilogue e;
       e.residual = dx;
@@ -510,10 +527,27 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
       }
       WB_CK(cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming));
     }
+    {
+      // B200, 224 greedy steps (tools/dec_groups.py): small B = 32 0.721 ms/step without, 0.703 / 0.701 / 0.700 / 0.713 /
+      // 0.729 with 24 / 32 / 48 / 72 / 96 MB per layer; medium B = 32 1.728 without, 1.693 / 1.691 / 1.715 / 1.808 / 1.888;
+      // large-v3 B = 15 2.122 without, 2.150 / 2.161 with 24 / 48 (its linears stream 50 MB of weights per layer and
+      // want the bandwidth themselves).  Identical token ids throughout.
+      static const int forced_mb = [] { const char* e = getenv("WB_DEC_PREFETCH_MB"); return e ? atoi(e) : -1; }();
+      const double layer_w_mb = 16.0 * hp.n_text_state * hp.n_text_state * 2.0 / (1 << 20);
+      const int pf_mb = forced_mb >= 0 ? forced_mb : (layer_w_mb <= 36.0 ? 32 : 0);
+      ctx->dec_pf_mb = pf_mb;
+      if (pf_mb > 0 && !ctx->dec_pf_stream) {
+        WB_CK(cudaStreamCreateWithFlags(&ctx->dec_pf_stream, cudaStreamNonBlocking));
+        WB_CK(cudaEventCreateWithFlags(&ctx->dec_pf_fork, cudaEventDisableTiming));
+        WB_CK(cudaEventCreateWithFlags(&ctx->dec_pf_join, cudaEventDisableTiming));
+      }
+    }
     WB_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
     if (n_groups <= 1) {
+      ctx->dec_pf_active = true;
       rc = decode_pass(ctx, ctx->d_next, n_seqs, 1);
+      ctx->dec_pf_active = false;
       if (rc == WB_OK) e1 = run_argmax(ctx, n_seqs, max_new, eot, 0, nullptr, 1);   // + the step's bookkeeping
     } else {
       // fork: every branch starts behind the previous step's bookkeeping on `st`; join: `st` waits for every branch
@@ -552,7 +586,8 @@ int wb_decode_greedy(wb_ctx* ctx, const int32_t* prompt, int n_prompt, int max_n
       WB_CK(cudaGraphLaunch(ctx->step_graph, st));
       // per layer: 6 linear + self-attn + cross-attn (LayerNorm folded into the linears); + embed, final LN,
       // logits, arg-max, advance
-      ctx->tm.n_kernel_launches += (8 * hp.n_text_layer + 4) * (n_groups > 1 ? (n_seqs + per_group - 1) / per_group : 1) + (n_groups > 1 ? 1 : 0);
+      ctx->tm.n_kernel_launches += (8 * hp.n_text_layer + 4) * (n_groups > 1 ? (n_seqs + per_group - 1) / per_group : 1) + (n_groups > 1 ? 1 : 0) +
+                                   (n_groups <= 1 && ctx->dec_pf_mb > 0 ? hp.n_text_layer : 0);   // + the L2 prefetch branch
     } else {
       if ((rc = decode_pass(ctx, ctx->d_next, n_seqs, 1))) return rc;
       LaunchTimer t(ctx, "dec_argmax");

@@ -230,5 +230,6 @@ cudaError_t launch_argmax_partials(const float* part, int n_part, int n_seq, int
                                    int* out_tokens, float* out_margin, int* out_len, int* done, int max_new,
                                    int* step_dev, int eot, cudaStream_t st, int* n_past_dev = nullptr, int advance_by = 0);
 cudaError_t launch_advance(int* n_past_dev, int add, int* step_dev, cudaStream_t st);
+cudaError_t launch_l2_prefetch(const void* p0, const void* p1, size_t bytes_each, cudaStream_t st);   // two ranges, 4 KB granules
 
 }  // namespace wb
