@@ -64,6 +64,25 @@ def test_cabi_exports_every_declared_symbol(pkg):
     assert b"sm_100a" in L.wb_version()
 
 
+def test_rust_sys_crate_declares_the_header(pkg):
+    """The reference-language binding (whisper.rs_b200/rust/whisper-b200-sys, source only: no rustc in this image) has
+    to stay in step with include/whisper_b200.h: every exported entry point except the developer hooks is declared, and
+    the config struct carries the header's fields in the header's order."""
+    import os
+    import re
+    from whisper_rs_b200 import cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rs = open(os.path.join(root, "whisper.rs_b200", "rust", "whisper-b200-sys", "src", "lib.rs")).read()
+    hdr = open(os.path.join(root, "include", "whisper_b200.h")).read()
+    hooks = {"wb_dbg_attention", "wb_dbg_gemm", "wb_dbg_layernorm", "wb_kernel_time_us"}
+    missing = [n for n in cabi.declared_symbols() if n not in hooks and not re.search(r"fn\s+%s\s*\(" % n, rs)]
+    assert not missing, missing
+    c_fields = re.findall(r"\b(?:int32_t|int64_t|int|void\s*\*)\s*(\w+)\s*(?:\[\d+\])?;",
+                          hdr[hdr.index("typedef struct wb_config"):hdr.index("} wb_config;")])
+    r_fields = re.findall(r"pub\s+(\w+)\s*:", rs[rs.index("pub struct wb_config"):rs.index("}", rs.index("pub struct wb_config"))])
+    assert c_fields and c_fields == r_fields, (c_fields, r_fields)
+
+
 def test_cabi_loader_errors_and_no_cpu_fallback(pkg, model_path, tmp_path):
     """Loader errors surface as WsError variants; with no GPU the product refuses to run
     (WsError::WrongGTensor) instead of falling back to a CPU path."""
